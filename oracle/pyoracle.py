@@ -1,0 +1,247 @@
+"""ctypes bindings for the CPU oracle -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` leg may import this module.  The product package
+(``singlecarrier_b200``) never does.
+
+Two libraries:
+
+* ``libsc_oracle.so``   -- the restatement (``oracle/sc_oracle.c``), buildable anywhere gcc is.
+* ``_ref/libsc_ref.so`` -- the reference's own sources compiled from ``/root/reference`` (only
+  buildable in the build container; travels to the GPU box as a prebuilt file).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "libsc_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libsc_ref.so")
+
+FRAME_SIZE = 1880
+BITS_PER_CALL = 62
+PREAMBLE_LENGTH = 128
+DATA_SYMBOLS = 31
+NTAPS = 49
+
+
+def build(quiet: bool = True) -> None:
+    """(Re)build the oracle, and the reference library when /root/reference is present."""
+    subprocess.run(["make", "-C", HERE, "all"], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+class FrameStats(C.Structure):
+    """sco_frame_stats (oracle/sc_oracle.h)."""
+    _fields_ = [("valid", C.c_int32), ("max_index", C.c_int32), ("matches", C.c_int32),
+                ("rx_timing", C.c_int32), ("max_value", C.c_float), ("cost", C.c_float),
+                ("eq_coeff", C.c_float * 10)]
+
+
+STATS_DTYPE = np.dtype([("valid", "<i4"), ("max_index", "<i4"), ("matches", "<i4"),
+                        ("rx_timing", "<i4"), ("max_value", "<f4"), ("cost", "<f4"),
+                        ("eq_coeff", "<f4", (10,))])
+assert STATS_DTYPE.itemsize == C.sizeof(FrameStats)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Oracle:
+    """The restatement library."""
+
+    def __init__(self, path: str = ORACLE_SO):
+        if not os.path.exists(path):
+            build()
+        self.lib = L = C.CDLL(path)
+        L.sco_sizeof_state.restype = C.c_ulong
+        L.sco_run_streams.restype = C.c_long
+        L.sco_run_streams.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.sco_run_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+        L.sco_init.argtypes = [C.c_void_p, C.c_int, C.c_float]
+        L.sco_rx_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sco_tx_preamble.argtypes = [C.c_void_p, C.c_void_p]
+        L.sco_tx_data.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.sco_tx_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.sco_fir.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.sco_correlate.restype = C.c_float
+        L.sco_correlate.argtypes = [C.c_void_p, C.c_int]
+        L.sco_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sco_kalman_init.argtypes = [C.c_void_p]
+        L.sco_kalman_reset.argtypes = [C.c_void_p]
+        L.sco_kalman_calculate.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.sco_train_eq.restype = C.c_float
+        L.sco_train_eq.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float]
+        L.sco_data_eq.restype = C.c_float
+        L.sco_data_eq.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.sco_scramble2.argtypes = [C.c_void_p, C.c_void_p]
+        L.sco_nco_rect.argtypes = [C.c_float, C.c_void_p]
+        self.state_size = int(L.sco_sizeof_state())
+
+    # ---- whole streams -------------------------------------------------------------------
+    def run_stream(self, samples: np.ndarray, wide: bool = False, foffset: float = 0.0):
+        """Cold-start one stream through sco_rx_frame; returns (bits[nf,62] (255 = invalid row), stats[nf])."""
+        x = np.ascontiguousarray(samples, dtype="<i2")
+        nf = x.size // FRAME_SIZE
+        bits = np.full((nf, BITS_PER_CALL), 255, np.uint8)
+        stats = np.zeros(nf, STATS_DTYPE)
+        self.lib.sco_run_stream(_p(x), nf, int(wide), float(foffset), _p(bits), _p(stats))
+        return bits, stats
+
+    def run_streams(self, samples: np.ndarray, n_frames: int, wide: bool = False):
+        """samples[n_streams, >= n_frames*1880] -> (bits[ns,nf,62], valid[ns,nf])."""
+        x = np.ascontiguousarray(samples, dtype="<i2")
+        ns, stride = x.shape
+        bits = np.full((ns, n_frames, BITS_PER_CALL), 255, np.uint8)
+        valid = np.zeros((ns, n_frames), np.int32)
+        self.lib.sco_run_streams(_p(x), ns, stride, n_frames, int(wide), _p(bits), _p(valid))
+        return bits, valid
+
+    # ---- stateful single-stream object ---------------------------------------------------
+    def new_state(self, wide: bool = False, foffset: float = 0.0):
+        buf = np.zeros(self.state_size + 64, np.uint8)
+        self.lib.sco_init(_p(buf), int(wide), float(foffset))
+        return buf
+
+    def rx_frame(self, state, frame: np.ndarray):
+        x = np.ascontiguousarray(frame, dtype="<i2")
+        assert x.size == FRAME_SIZE
+        bits = np.full(BITS_PER_CALL, 255, np.uint8)
+        st = np.zeros(1, STATS_DTYPE)
+        self.lib.sco_rx_frame(_p(state), _p(x), _p(bits), _p(st))
+        return bits, st[0]
+
+    def tx_preamble(self, state) -> np.ndarray:
+        out = np.zeros(PREAMBLE_LENGTH * 5, "<i2")
+        self.lib.sco_tx_preamble(_p(state), _p(out))
+        return out
+
+    def tx_data(self, state, bits: np.ndarray) -> np.ndarray:
+        b = np.ascontiguousarray(bits, np.uint8)
+        nsym = b.size // 2
+        out = np.zeros(nsym * 5, "<i2")
+        self.lib.sco_tx_data(_p(state), _p(out), _p(b), nsym)
+        return out
+
+    # ---- stage primitives ----------------------------------------------------------------
+    def fir(self, memory: np.ndarray, wide: bool, sample: np.ndarray):
+        """In place on complex64 arrays (memory[49], sample[n])."""
+        assert memory.dtype == np.complex64 and sample.dtype == np.complex64
+        self.lib.sco_fir(_p(memory), int(wide), _p(sample), sample.size)
+
+    def search(self, symbols: np.ndarray):
+        s = np.ascontiguousarray(symbols, np.complex64)
+        assert s.size >= 255
+        idx = C.c_int32(0)
+        val = C.c_float(0)
+        self.lib.sco_search(_p(s), C.byref(idx), C.byref(val))
+        return idx.value, np.float32(val.value)
+
+    def correlate(self, symbols: np.ndarray, lag: int) -> np.float32:
+        s = np.ascontiguousarray(symbols, np.complex64)
+        return np.float32(self.lib.sco_correlate(_p(s), lag))
+
+    def nco_rect(self, freq_hz: float) -> np.complex64:
+        out = np.zeros(1, np.complex64)
+        self.lib.sco_nco_rect(float(freq_hz), _p(out))
+        return out[0]
+
+
+class RefStats(C.Structure):
+    """ref_frame_stats (oracle/ref_harness_post.c)."""
+    _fields_ = [("valid", C.c_int32), ("max_index", C.c_int32), ("matches", C.c_int32),
+                ("rx_timing", C.c_int32), ("max_value", C.c_float), ("mean", C.c_float),
+                ("eq_coeff", C.c_float * 10)]
+
+
+REF_STATS_DTYPE = np.dtype([("valid", "<i4"), ("max_index", "<i4"), ("matches", "<i4"),
+                            ("rx_timing", "<i4"), ("max_value", "<f4"), ("mean", "<f4"),
+                            ("eq_coeff", "<f4", (10,))])
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+class Reference:
+    """The reference's own object code (process-global state: one stream at a time)."""
+
+    def __init__(self, path: str = REF_SO):
+        self.lib = L = C.CDLL(path)
+        L.ref_reset.argtypes = [C.c_int]
+        L.ref_rx_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_run_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_run_streams.restype = C.c_long
+        L.ref_run_streams.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_tx_preamble.argtypes = [C.c_void_p]
+        L.ref_tx_data.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_get_filtered.argtypes = [C.c_void_p, C.c_int]
+        L.ref_get_decimated.argtypes = [C.c_void_p, C.c_int]
+        L.fir.argtypes = [C.c_void_p, C.c_bool, C.c_void_p, C.c_int]
+        L.train_eq.restype = C.c_float
+        L.train_eq.argtypes = [C.c_void_p, C.c_int, C.c_float]
+        L.data_eq.restype = C.c_float
+        L.data_eq.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.kalman_calculate.argtypes = [C.c_void_p, C.c_int]
+        L.scramble_init.argtypes = [C.c_int]
+        L.scramble.argtypes = [C.c_void_p, C.c_int]
+
+    def reset(self, wide: bool = False):
+        self.lib.ref_reset(int(wide))
+
+    def run_stream(self, samples: np.ndarray, wide: bool = False):
+        x = np.ascontiguousarray(samples, dtype="<i2")
+        nf = x.size // FRAME_SIZE
+        bits = np.full((nf, BITS_PER_CALL), 255, np.uint8)
+        stats = np.zeros(nf, REF_STATS_DTYPE)
+        self.lib.ref_run_stream(_p(x), nf, int(wide), _p(bits), _p(stats))
+        return bits, stats
+
+    def run_streams(self, samples: np.ndarray, n_frames: int, wide: bool = False):
+        x = np.ascontiguousarray(samples, dtype="<i2")
+        ns, stride = x.shape
+        bits = np.full((ns, n_frames, BITS_PER_CALL), 255, np.uint8)
+        valid = np.zeros((ns, n_frames), np.int32)
+        self.lib.ref_run_streams(_p(x), ns, stride, n_frames, int(wide), _p(bits), _p(valid))
+        return bits, valid
+
+    def rx_frame(self, frame: np.ndarray):
+        x = np.ascontiguousarray(frame, dtype="<i2")
+        bits = np.full(496, 255, np.uint8)
+        st = np.zeros(1, REF_STATS_DTYPE)
+        self.lib.ref_rx_frame(_p(x), _p(bits), _p(st))
+        return bits[:BITS_PER_CALL], st[0]
+
+    def filtered(self, n: int = FRAME_SIZE) -> np.ndarray:
+        out = np.zeros(n, np.complex64)
+        self.lib.ref_get_filtered(_p(out), n)
+        return out
+
+    def decimated(self, n: int = 752) -> np.ndarray:
+        out = np.zeros(n, np.complex64)
+        self.lib.ref_get_decimated(_p(out), n)
+        return out
+
+    def tx_preamble(self) -> np.ndarray:
+        out = np.zeros(PREAMBLE_LENGTH * 5, "<i2")
+        self.lib.ref_tx_preamble(_p(out))
+        return out
+
+    def tx_data(self, bits: np.ndarray) -> np.ndarray:
+        b = np.ascontiguousarray(bits, np.uint8).copy()
+        nsym = b.size // 2
+        out = np.zeros(nsym * 5, "<i2")
+        self.lib.ref_tx_data(_p(out), _p(b), nsym)
+        return out
+
+    def global_c32(self, name: str, n: int) -> np.ndarray:
+        arr = (C.c_float * (2 * n)).in_dll(self.lib, name)
+        return np.frombuffer(arr, np.float32).view(np.complex64)
+
+    def global_f32(self, name: str) -> C.c_float:
+        return C.c_float.in_dll(self.lib, name)
