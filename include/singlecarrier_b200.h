@@ -1,0 +1,188 @@
+/*
+ * singlecarrier_b200.h -- C ABI of libsinglecarrier_b200.so (batched, handle based).
+ *
+ * The reference (srsampson/SingleCarrier) has no plugin/FFI layer: its boundary is its seven
+ * headers and one global-state stream per process.  This library keeps those symbols as a
+ * drop-in (see include/sc_compat/ *.h: fir.h, equalizer.h, kalman.h, scramble.h, fft.h,
+ * qpsk_internal.h) and adds the batched layer below, which is what a caller binds to when it
+ * has thousands of independent 8 kHz streams.  Plain pointers and sizes only; no torch types.
+ *
+ * A "modem bank" is N synchronized streams.  Every stream of a bank is at the same call index
+ * n (number of qpsk_rx_frame() calls made so far), exactly like N copies of the reference
+ * process fed in lock step.  Each entry point cites the reference interface it replaces.
+ *
+ * All functions return SC_OK (0) or a negative SC_E* code; sc_last_error() gives the text.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * SC_ECUDA.
+ */
+#ifndef SINGLECARRIER_B200_H
+#define SINGLECARRIER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SC_FRAME_SIZE        1880   /* samples per qpsk_rx_frame() call, qpsk_internal.h:47 */
+#define SC_SYMBOLS_PER_FRAME 376    /* FRAME_SIZE / CYCLES                                   */
+#define SC_PREAMBLE_LENGTH   128    /* qpsk_internal.h:52                                    */
+#define SC_DATA_SYMBOLS      31     /* qpsk_internal.h:40                                    */
+#define SC_BITS_PER_CALL     62     /* decided bits per valid call               */
+#define SC_NTAPS             49     /* fir.h:16                                              */
+#define SC_EQ_LENGTH         5      /* kalman.h:26                                           */
+#define SC_PACKET_SYMBOLS    376    /* 128 preamble + 8 x 31 data                            */
+
+#define SC_OK        0
+#define SC_EINVAL   -1
+#define SC_ECUDA    -2
+#define SC_ENOMEM   -3
+#define SC_ESTATE   -4
+
+#define SC_FLAG_WIDE      0x1u      /* firwide=true: alpha=0.5 taps (qpsk.c:60)              */
+#define SC_FLAG_DEBUG_EQ  0x2u      /* keep eq_coeff[5] of every call (parity tests)         */
+
+typedef struct sc_modem sc_modem;
+
+/*
+ * Result of one qpsk_rx_frame() call of one stream (32 bytes, one DRAM sector).
+ *   bits      bit k = bits[k] of the reference's output row: bits[2i] = Q, bits[2i+1] = I of
+ *             data symbol i, descrambled (qpsk.c:206-215).  Decided for invalid calls too
+ *             (the reference computes and discards them, qpsk.c:225-229).
+ *   cost      valid: the DEBUG2 "Mean" = magnitude() (qpsk.c:190); invalid: the summed
+ *             data_eq() returns tested against EOF_COST_VALUE (qpsk.c:223-235).
+ *   rx_timing the static rx_timing AFTER the call (qpsk.c:219).
+ */
+typedef struct {
+    uint64_t bits;
+    float    max_value;     /* correlate() maximum, qpsk.c:176-183 */
+    float    cost;
+    int16_t  max_index;
+    int16_t  matches;       /* equalize() return, qpsk.c:188       */
+    int16_t  rx_timing;
+    uint8_t  valid;         /* qpsk_rx_frame() return value         */
+    uint8_t  reserved0;
+    uint32_t call_index;    /* n, counted from the bank's cold start */
+    uint32_t reserved1;
+} sc_frame_result;
+
+/* ---- life cycle ------------------------------------------------------------------------ */
+
+/* Replaces the start-up block of main(), qpsk.c:361-368,427-434: cold state for n_streams
+ * streams on CUDA device `device`.  foffset_hz is the reference's FOFFSET macro (qpsk.c:67). */
+int  sc_create(sc_modem **out, int device, int64_t n_streams, uint32_t flags, float foffset_hz);
+void sc_destroy(sc_modem *m);
+int  sc_reset(sc_modem *m);                       /* back to call index 0, cold state */
+int64_t  sc_n_streams(const sc_modem *m);
+uint32_t sc_call_index(const sc_modem *m);
+const char *sc_last_error(void);
+const char *sc_version(void);
+int  sc_device_count(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+uint64_t sc_launch_count(void);
+
+/* ---- RX: replaces the while(1) loop of main() calling qpsk_rx_frame(), qpsk.c:436-458 --- */
+
+/*
+ * n_frames calls per stream.  Stream s, call j reads 1880 int16 at in + s*stream_stride +
+ * j*1880 (stream_stride in samples, >= n_frames*1880).  results[s*result_stride + j] receives
+ * the call's result (result_stride in records, >= n_frames).  eq_dbg (may be NULL; needs
+ * SC_FLAG_DEBUG_EQ) receives eq_coeff[5] as 10 floats at (s*result_stride + j)*10.
+ *
+ * _dev: all pointers are device pointers on the bank's device; work is ordered after
+ *       everything already queued on `stream` (a cudaStream_t) and `stream` waits for it.
+ * _host: all pointers are host pointers (pinned gives asynchronous copies); host->device
+ *        copies of the samples and device->host copies of the results are pipelined with the
+ *        kernels in slabs of streams; returns after everything has landed.
+ */
+int sc_rx_frames_dev(sc_modem *m, const int16_t *in, int64_t stream_stride, int n_frames,
+                     sc_frame_result *results, int64_t result_stride, float *eq_dbg, void *stream);
+int sc_rx_frames_host(sc_modem *m, const int16_t *in, int64_t stream_stride, int n_frames,
+                      sc_frame_result *results, int64_t result_stride, float *eq_dbg);
+
+/* Host helper: unpack results into the reference's on-disk format (qpsk.c:455-457): for every
+ * VALID call, 62 bytes (0/1) are written to rows + (s*n_frames + j)*62; other rows untouched. */
+void sc_unpack_bits(const sc_frame_result *results, int64_t n_records, uint8_t *rows);
+
+/* ---- TX: replaces preamble_modulate()/qpsk_modulate()/qpsk_tx_frame(), qpsk.c:278-342 ---- */
+
+/*
+ * Synthesize n_packets packets per stream exactly as main() does (qpsk.c:380-413): per packet
+ * one 640-sample BPSK preamble at half amplitude, eight 155-sample QPSK data frames built from
+ * bits (62 bytes of 0/1 per data frame: bits[2i] = Q, bits[2i+1] = I, qpsk.c:251-256), then
+ * gap_samples zeros that do NOT pass through the filter or the NCO (qpsk.c:410-412; the
+ * reference uses 903).  lead_in[s] zeros precede the first packet of stream s (NULL = 0).
+ * tx_filter and fbb_tx_phase persist across frames and packets as in the reference.
+ *   bits: device pointer, [n_streams][n_packets][8][62] bytes, or NULL to draw them from the
+ *         counter-based generator seeded with `seed` (returned through bits_out if not NULL,
+ *         same layout).
+ *   out : device pointer, stream s at out + s*stream_stride; samples beyond the last packet
+ *         up to samples_per_stream are zero filled.
+ * The bank's TX state is cold at the start of the call (one call = one whole transmission).
+ */
+int sc_tx_packets_dev(sc_modem *m, const uint8_t *bits, uint8_t *bits_out, uint64_t seed,
+                      int n_packets, int gap_samples, const int32_t *lead_in,
+                      int16_t *out, int64_t stream_stride, int64_t samples_per_stream, void *stream);
+
+/*
+ * Channel for synthetic loop-back (BASELINE.json configs 2-5; no counterpart in the reference
+ * beyond FOFFSET): same synthesis as sc_tx_packets_dev, but the analytic TX signal of stream s
+ * is rotated by exp(j(2*pi*(df[s] + 0.5*drift[s]*t)*t + phi[s])) (t in seconds), optionally passed
+ * through a 2-tap channel h = [1, a[s]*exp(j*theta[s])] at delay d[s] samples, and real AWGN of
+ * standard deviation sigma[s] (in int16 LSB) is added before saturating to int16.  Any of the
+ * per-stream parameter arrays (device pointers) may be NULL (= 0).
+ */
+typedef struct {
+    const float   *df_hz;       /* frequency offset                  */
+    const float   *phi_rad;     /* phase offset                      */
+    const float   *drift_hz_s;  /* linear frequency drift            */
+    const float   *sigma_lsb;   /* AWGN standard deviation, int16 LSB */
+    const float   *echo_amp;    /* second path amplitude a           */
+    const float   *echo_theta;  /* second path phase                 */
+    const int32_t *echo_delay;  /* second path delay in samples (1..16) */
+} sc_channel;
+
+int sc_tx_channel_dev(sc_modem *m, const uint8_t *bits, uint8_t *bits_out, uint64_t seed,
+                      int n_packets, int gap_samples, const int32_t *lead_in, const sc_channel *ch,
+                      int16_t *out, int64_t stream_stride, int64_t samples_per_stream, void *stream);
+
+/* ---- stage entry points (device pointers; batched forms of the reference's L1 functions) -- */
+
+/* fir(), fir.h:19 / src/fir.c:22-44, for n_streams independent (memory, sample) pairs:
+ * memory[s*49 .. +49), sample[s*sample_stride .. +length) complex float, both updated in place. */
+int sc_fir_batch_dev(int device, int64_t n_streams, int wide, float *memory, float *sample,
+                     int64_t sample_stride, int length, void *stream);
+
+/* correlate() + argmax, qpsk.c:88-96,172-183: symbols[s*symbol_stride .. +255) complex float
+ * -> max_index[s], max_value[s]. */
+int sc_preamble_search_batch_dev(int device, int64_t n_streams, const float *symbols,
+                                 int64_t symbol_stride, int32_t *max_index, float *max_value,
+                                 void *stream);
+
+/* kalman_reset() + equalize() + the data_eq() loop, qpsk.c:186-236: the decision half of one
+ * qpsk_rx_frame() call on an explicit symbol window.  symbols[s*symbol_stride .. +290) complex
+ * float, max_index[s] from the search, rx_timing[s] at entry, keystream position = call_index.
+ * results[s] as above, rx_timing[s] updated in place. */
+int sc_track_decide_batch_dev(int device, int64_t n_streams, const float *symbols,
+                              int64_t symbol_stride, const int32_t *max_index, const float *max_value,
+                              int32_t *rx_timing, uint32_t call_index, sc_frame_result *results,
+                              float *eq_dbg, void *stream);
+
+/* fft(), fft.h:46: n_batches independent length-nfft complex FFTs (nfft a power of two,
+ * 2..4096), out-of-place or in-place (in == out), unnormalised inverse like the reference. */
+int sc_fft_batch_dev(int device, int64_t n_batches, int nfft, int inverse, const float *in,
+                     float *out, void *stream);
+
+/* ---- small utilities used by host code and tests --------------------------------------- */
+
+/* RX/TX NCO phasor table exactly as the reference's recurrences generate it (qpsk.c:138-147,
+ * 301-306): out[f*1880 + i] = phasor used for sample i of call f (f = first_call ..). Host out. */
+int sc_nco_table_host(sc_modem *m, int tx, uint32_t first_call, int n_calls, float *out);
+/* descrambler keystream word of call n (62 bits), src/scramble.c:57-69 seeded at qpsk.c:434 */
+uint64_t sc_keystream_word(uint32_t call_index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,54 @@
+// sc_kernels.h -- launcher prototypes shared between the kernel translation units and sc_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/singlecarrier_b200.h"
+
+namespace sc {
+
+extern unsigned long long g_launch_count;
+
+// sc_rx_kernels.cu
+cudaError_t launch_nco_table(float2 *phase_state, float2 rect, const int *seg_len, int n_seg, float scale,
+                             float2 *out, cudaStream_t st);
+cudaError_t launch_frontend(bool wide, const int16_t *in, long stream_stride, const float2 *mix_table,
+                            const int *timing_cur, const int *timing_next, float2 *win, int *max_index,
+                            float *max_value, int n_streams, cudaStream_t st);
+cudaError_t launch_track(bool debug_eq, const float2 *win, const int *max_index, const float *max_value,
+                         const int *timing_cur, int *timing_next, sc_frame_result *results, long result_stride,
+                         float *eq_dbg, uint32_t call_index, unsigned long long keystream, int n_streams,
+                         cudaStream_t st);
+
+// sc_stage_kernels.cu
+cudaError_t launch_fir_batch(bool wide, long n_streams, float2 *memory, float2 *sample, long sample_stride,
+                             int length, cudaStream_t st);
+cudaError_t launch_search_batch(long n_streams, const float2 *symbols, long symbol_stride, int *max_index,
+                                float *max_value, cudaStream_t st);
+cudaError_t launch_track_window_batch(long n_streams, const float2 *symbols, long symbol_stride,
+                                      const int *max_index, const float *max_value, int *rx_timing,
+                                      uint32_t call_index, unsigned long long keystream,
+                                      sc_frame_result *results, float *eq_dbg, cudaStream_t st);
+cudaError_t launch_fft_batch(long n_batches, int nfft, int inverse, const float2 *in, float2 *out,
+                             cudaStream_t st);
+
+// sc_tx_kernels.cu
+struct TxArgs {
+    const uint8_t *bits;        // [n][n_packets][8][62] or nullptr
+    uint8_t *bits_out;          // same layout or nullptr
+    unsigned long long seed;
+    int n_packets;
+    int gap_samples;
+    const int *lead_in;         // [n] or nullptr
+    const float2 *tx_table;     // [n_packets*1880] TX NCO phasors
+    int16_t *out;
+    long stream_stride;
+    long samples_per_stream;
+    long n_streams;
+    bool wide;
+    bool use_channel;
+    sc_channel ch;
+};
+cudaError_t launch_tx(const TxArgs &a, cudaStream_t st);
+
+}  // namespace sc

@@ -1,0 +1,358 @@
+// sc_rx_kernels.cu -- the RX hot path as hand-written sm_100a kernels.
+//
+// One qpsk_rx_frame() call of the reference (src/qpsk.c:133-239) over a bank of N streams is two
+// launches:
+//   track_kernel     (one thread per stream)  kalman_reset -> 128 x train_eq -> 31 x data_eq ->
+//                    slice -> descramble on the symbol window prepared by the previous call;
+//   frontend_kernel  (one warp per stream)    int16 -> mix -> 49-tap RRC evaluated only at the
+//                    <= 290 decimated instants the reference can ever read -> 128-lag preamble
+//                    correlation + first-maximum argmax -> tracker window for the next call.
+// plus two tiny table kernels (NCO phasors; data independent, shared by all streams).
+#include "sc_common.cuh"
+#include "sc_tables.cuh"
+#include "sc_tracker.cuh"
+#include "sc_kernels.h"
+
+namespace sc {
+
+__constant__ uint32_t c_pre_neg[4] = {pre_neg_word(0), pre_neg_word(1), pre_neg_word(2), pre_neg_word(3)};
+
+// ------------------------------------------------------------------------------------------------
+// NCO phasor table.  The reference advances one complex phasor per sample by a float recurrence
+// and renormalises it after every frame (qpsk.c:138-147 RX, :301-306 TX).  The sequence does not
+// depend on the data, so it is generated once per batch by a single thread running the identical
+// recurrence and shared by every stream.  seg_len[] lists the run lengths between renormalisations
+// (RX: 1880 per call; TX: 640,155 x 8 per packet).  scale multiplies the stored value (a power of
+// two, exact): the RX table is stored pre-multiplied by 1/16384 so the mixer is phasor*(float)in.
+// ------------------------------------------------------------------------------------------------
+__global__ void nco_table_kernel(float2 *__restrict__ phase_state, float2 rect, const int *__restrict__ seg_len,
+                                 int n_seg, float scale, float2 *__restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    c32 ph = from2(*phase_state);
+    const c32 r = from2(rect);
+    long k = 0;
+    for (int s = 0; s < n_seg; s++) {
+        const int len = seg_len[s];
+        for (int i = 0; i < len; i++, k++) {
+            ph = cmul(ph, r);
+            out[k] = make_float2(__fmul_rn(ph.r, scale), __fmul_rn(ph.i, scale));
+        }
+        ph = renorm(ph);
+    }
+    *phase_state = to2(ph);
+}
+
+// ------------------------------------------------------------------------------------------------
+// frontend_kernel: one warp per stream, FE_WARPS streams per CTA.
+//
+// Needed input: decimated instant i of the older half is filtered sample 5i + T (T = rx_timing at
+// entry, qpsk.c:161), which depends on mixed samples 5i+T-48 .. 5i+T (src/fir.c: memory[] holds raw
+// inputs, so any output can be evaluated on its own, bit-exactly).  For i < 290 that is the sample
+// range [T-48, T+1445] of ONE frame (T >= 128 after the first call), 1494 samples.
+//
+// Shared memory per warp: the mixed samples as float2 with one pad slot every 50 samples
+// (pos = rel + rel/50), so that lane l, which evaluates outputs 10l..10l+9 and therefore reads
+// samples 50l .. 50l+93, has a lane stride of 51 slots (odd => conflict free 64-bit reads) and
+// compile-time offsets.  The region is then reused for W[290] and the (d,e) search operands.
+// ------------------------------------------------------------------------------------------------
+constexpr int FE_WARPS = 4;
+constexpr int FE_NSAMP = NTAPS + CYC * (WIN - 1);          // 1494
+constexpr int FE_MIX_SLOTS = FE_NSAMP + FE_NSAMP / 50 + 2; // 1525 (+ spare)
+constexpr int FE_OUT_PER_LANE = 10;
+constexpr int FE_FIR_LANES = WIN / FE_OUT_PER_LANE;        // 29
+constexpr int FE_DE_SLOTS = 320;                            // pos(x) = x + x/4, x < 255
+static_assert(WIN == FE_FIR_LANES * FE_OUT_PER_LANE, "290 = 29 x 10");
+static_assert(290 + FE_DE_SLOTS <= FE_MIX_SLOTS, "W and (d,e) reuse the mixed-sample region");
+
+template <bool WIDE>
+__global__ void __launch_bounds__(FE_WARPS * 32)
+frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2 *__restrict__ mix_table,
+                const int *__restrict__ timing_cur, const int *__restrict__ timing_next,
+                float2 *__restrict__ win, int *__restrict__ max_index_out, float *__restrict__ max_value_out,
+                int n_streams) {
+    __shared__ __align__(16) float2 smem[FE_WARPS][FE_MIX_SLOTS];
+    __shared__ int s_maxidx[FE_WARPS];
+    __shared__ int s_t2[FE_WARPS];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long s = (long) blockIdx.x * FE_WARPS + warp;
+    const bool active = s < n_streams;
+    float2 *mix = smem[warp];
+
+    if (active) {
+        const int T = timing_cur[s];
+        const int base = T - (NTAPS - 1);              // first sample needed (may be < 0 only if T < 48)
+        const int16_t *frame = in + s * stream_stride;
+
+        // ---- stage 1: load int16, mix to baseband, stage in shared memory (qpsk.c:138-145) ----
+        if ((((uintptr_t) frame) & 15) == 0) {
+            const int c0 = (base < 0 ? 0 : base) >> 3;
+            const int c1 = (base + FE_NSAMP - 1) >> 3;
+            for (int c = c0 + lane; c <= c1; c += 32) {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(frame) + c);
+                const float4 *tp = reinterpret_cast<const float4 *>(mix_table + c * 8);
+                const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+                const int rel0 = c * 8 - base;
+#pragma unroll
+                for (int h = 0; h < 4; h++) {
+                    const float4 ph = __ldg(tp + h);
+                    const float v0 = (float) (int16_t) (w[h] & 0xffffu);
+                    const float v1 = (float) (int16_t) (w[h] >> 16);
+                    const int r0 = rel0 + 2 * h, r1 = r0 + 1;
+                    if (r0 >= 0 && r0 < FE_NSAMP)
+                        mix[r0 + r0 / 50] = make_float2(__fmul_rn(ph.x, v0), __fmul_rn(ph.y, v0));
+                    if (r1 >= 0 && r1 < FE_NSAMP)
+                        mix[r1 + r1 / 50] = make_float2(__fmul_rn(ph.z, v1), __fmul_rn(ph.w, v1));
+                }
+            }
+        } else {
+            for (int rel = lane; rel < FE_NSAMP; rel += 32) {
+                const int t = base + rel;
+                if (t >= 0) {
+                    const float v = (float) frame[t];
+                    const float2 ph = __ldg(mix_table + t);
+                    mix[rel + rel / 50] = make_float2(__fmul_rn(ph.x, v), __fmul_rn(ph.y, v));
+                }
+            }
+        }
+        if (base < 0) {   // cold-start timing only: samples before the frame are taken as silence
+            for (int rel = lane; rel < -base && rel < FE_NSAMP; rel += 32) mix[rel + rel / 50] = make_float2(0.f, 0.f);
+        }
+    }
+    __syncwarp();
+
+    // ---- stage 2: 49-tap RRC at 10 consecutive decimated instants per lane (src/fir.c:36-42) ----
+    u64 acc[FE_OUT_PER_LANE];
+#pragma unroll
+    for (int r = 0; r < FE_OUT_PER_LANE; r++) acc[r] = 0ull;
+
+    if (active && lane < FE_FIR_LANES) {
+        const u64 *mp = reinterpret_cast<const u64 *>(mix) + 51 * lane;
+#pragma unroll
+        for (int j = 0; j < NTAPS + CYC * (FE_OUT_PER_LANE - 1); j++) {
+            const u64 x = mp[j + (j >= 50 ? 1 : 0)];
+#pragma unroll
+            for (int r = 0; r < FE_OUT_PER_LANE; r++) {
+                const int k = j - CYC * r;
+                if (k >= 0 && k < NTAPS) acc[r] = pk_add(acc[r], pk_mul_bcast_pz(x, tap<WIDE>(k)));
+            }
+        }
+    }
+    __syncwarp();
+
+    float2 *W = mix;                       // [290]
+    float2 *DE = mix + WIN;                // [320], pos(x) = x + x/4
+    if (active && lane < FE_FIR_LANES) {
+#pragma unroll
+        for (int r = 0; r < FE_OUT_PER_LANE; r++) {
+            float yr, yi;
+            unpk(acc[r], yr, yi);
+            W[FE_OUT_PER_LANE * lane + r] = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));
+        }
+    }
+    __syncwarp();
+
+    // ---- stage 3: preamble search (qpsk.c:88-96, 172-183) ----
+    // pre[i] = v(1+1i), v = +-1  =>  pre[i]*s = v*(s.r - s.i) + i*v*(s.i + s.r) exactly, so keep
+    // d = s.r - s.i, e = s.i + s.r once per symbol and accumulate +-(d,e) in the reference's order.
+    if (active) {
+        for (int x = lane; x < 255; x += 32) {
+            const float2 w = W[x];
+            DE[x + (x >> 2)] = make_float2(__fsub_rn(w.x, w.y), __fadd_rn(w.y, w.x));
+        }
+    }
+    __syncwarp();
+
+    int best_idx = 0;
+    float best_val = 0.0f;
+    if (active) {
+        u64 a[4] = {0ull, 0ull, 0ull, 0ull};
+        const u64 *dp = reinterpret_cast<const u64 *>(DE) + 5 * lane;     // lags 4*lane .. 4*lane+3
+#pragma unroll
+        for (int j = 0; j < PRE + 3; j++) {
+            const u64 v = dp[j + (j >> 2)];
+#pragma unroll
+            for (int qd = 0; qd < 4; qd++) {
+                const int i = j - qd;
+                if (i >= 0 && i < PRE) a[qd] = pre_neg(i) ? pk_sub(a[qd], v) : pk_add(a[qd], v);
+            }
+        }
+#pragma unroll
+        for (int qd = 0; qd < 4; qd++) {
+            float re, im;
+            unpk(a[qd], re, im);
+            const float val = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));   // cnormf, qpsk.c:75-80
+            if (val > best_val) {
+                best_val = val;
+                best_idx = 4 * lane + qd;
+            }
+        }
+        // strict '>' with first maximum winning == largest value, smallest lag among ties
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best_val, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
+            if (ov > best_val || (ov == best_val && oi < best_idx)) {
+                best_val = ov;
+                best_idx = oi;
+            }
+        }
+        if (best_val == 0.0f) best_idx = 0;     // nothing ever exceeded the initial 0.0f
+        if (lane == 0) {
+            max_index_out[s] = best_idx;
+            max_value_out[s] = best_val;
+            s_maxidx[warp] = best_idx;
+            s_t2[warp] = timing_next[s];
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 4: hand the tracker its window, 32-byte sectors (4 adjacent streams per row) ----
+    {
+        const long s0 = (long) blockIdx.x * FE_WARPS;
+        const int j = threadIdx.x & (FE_WARPS - 1);
+        const long sj = s0 + j;
+        if (sj < n_streams) {
+            const int mi = s_maxidx[j], t2 = s_t2[j];
+            const float2 *Wj = smem[j];
+            float2 *dst = win + ((sj >> 5) * WIN_ROWS) * 32 + (sj & 31);
+            for (int row = threadIdx.x / FE_WARPS; row < WIN_ROWS; row += (FE_WARPS * 32) / FE_WARPS) {
+                int src = row < X_ROWS ? mi + row : t2 + (row - X_ROWS);
+                float2 v = make_float2(0.f, 0.f);
+                if (src >= 0 && src < WIN) v = Wj[src];
+                dst[row * 32] = v;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// track_kernel: one thread per stream; the decision half of qpsk_rx_frame(), qpsk.c:186-238.
+// ------------------------------------------------------------------------------------------------
+constexpr int TK_THREADS = 128;
+
+template <bool DEBUG_EQ>
+__global__ void __launch_bounds__(TK_THREADS)
+track_kernel(const float2 *__restrict__ win, const int *__restrict__ max_index, const float *__restrict__ max_value,
+             const int *__restrict__ timing_cur, int *__restrict__ timing_next, sc_frame_result *__restrict__ results,
+             long result_stride, float *__restrict__ eq_dbg, uint32_t call_index, unsigned long long keystream,
+             int n_streams) {
+    const long s = (long) blockIdx.x * TK_THREADS + threadIdx.x;
+    if (s >= n_streams) return;
+
+    const float2 *X = win + ((s >> 5) * WIN_ROWS) * 32 + (s & 31);
+
+    Tracker tk;
+    tk.reset();                                                    // qpsk.c:186
+
+    c32 x[EQ];
+#pragma unroll
+    for (int i = 0; i < EQ - 1; i++) x[i] = from2(X[i * 32]);
+
+    // equalize(), qpsk.c:111-123, and magnitude(), qpsk.c:101-109, in one pass
+    int matches = 0;
+    float mag = 0.0f;
+#pragma unroll 1
+    for (int i = 0; i < PRE; i++) {
+        x[EQ - 1] = from2(X[(i + EQ - 1) * 32]);
+        const float ref = ((c_pre_neg[i >> 5] >> (i & 31)) & 1u) ? -1.0f : 1.0f;
+        mag = __fadd_rn(mag, __fadd_rn(__fmul_rn(x[0].r, x[0].r), __fmul_rn(x[0].i, x[0].i)));
+        const float er = tk.train(x, ref);
+        if (__fmul_rn(er, ref) > 0.0f) matches++;
+#pragma unroll
+        for (int k = 0; k < EQ - 1; k++) x[k] = x[k + 1];
+    }
+
+    const bool valid = matches > MATCH_THRESHOLD;                  // qpsk.c:196
+    const int t_in = timing_cur[s];
+    const int mi = max_index[s];
+
+    // valid: data symbols follow the preamble (rows 128..); invalid: they start at rx_timing (rows 163..)
+    const float2 *Dw = valid ? X + PRE * 32 : X + X_ROWS * 32;
+#pragma unroll
+    for (int i = 0; i < EQ - 1; i++) x[i] = from2(Dw[i * 32]);
+
+    unsigned long long word = 0ull;
+    float cost = 0.0f;
+#pragma unroll 1
+    for (int i = 0; i < NDATA; i++) {
+        x[EQ - 1] = from2(Dw[(i + EQ - 1) * 32]);
+        int bI, bQ;
+        const float er = tk.data(x, bI, bQ);
+        cost = __fadd_rn(cost, er);                                // qpsk.c:228
+        word |= ((unsigned long long) (unsigned) (bQ | (bI << 1))) << (2 * i);   // bits[2i]=Q, bits[2i+1]=I
+#pragma unroll
+        for (int k = 0; k < EQ - 1; k++) x[k] = x[k + 1];
+    }
+
+    const int t_out = valid ? mi + PRE : t_in;                     // qpsk.c:219
+    timing_next[s] = t_out;
+
+    sc_frame_result r;
+    r.bits = word ^ keystream;                                     // scramble(bits, rx), equalizer.c:87
+    r.max_value = max_value[s];
+    r.cost = valid ? mag : cost;
+    r.max_index = (int16_t) mi;
+    r.matches = (int16_t) matches;
+    r.rx_timing = (int16_t) t_out;
+    r.valid = valid ? 1 : 0;
+    r.reserved0 = 0;
+    r.call_index = call_index;
+    r.reserved1 = 0;
+    uint4 *dst = reinterpret_cast<uint4 *>(results + s * result_stride);
+    const uint4 *srcp = reinterpret_cast<const uint4 *>(&r);
+    dst[0] = srcp[0];
+    dst[1] = srcp[1];
+
+    if (DEBUG_EQ && eq_dbg != nullptr) {
+        float *e = eq_dbg + s * result_stride * 10;
+#pragma unroll
+        for (int i = 0; i < EQ; i++) {
+            e[2 * i] = tk.C[i].r;
+            e[2 * i + 1] = tk.C[i].i;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers (called from sc_api.cu)
+// ------------------------------------------------------------------------------------------------
+extern unsigned long long g_launch_count;
+
+cudaError_t launch_nco_table(float2 *phase_state, float2 rect, const int *seg_len, int n_seg, float scale,
+                             float2 *out, cudaStream_t st) {
+    nco_table_kernel<<<1, 32, 0, st>>>(phase_state, rect, seg_len, n_seg, scale, out);
+    g_launch_count++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_frontend(bool wide, const int16_t *in, long stream_stride, const float2 *mix_table,
+                            const int *timing_cur, const int *timing_next, float2 *win, int *max_index,
+                            float *max_value, int n_streams, cudaStream_t st) {
+    const int grid = (n_streams + FE_WARPS - 1) / FE_WARPS;
+    if (wide)
+        frontend_kernel<true><<<grid, FE_WARPS * 32, 0, st>>>(in, stream_stride, mix_table, timing_cur, timing_next,
+                                                              win, max_index, max_value, n_streams);
+    else
+        frontend_kernel<false><<<grid, FE_WARPS * 32, 0, st>>>(in, stream_stride, mix_table, timing_cur, timing_next,
+                                                               win, max_index, max_value, n_streams);
+    g_launch_count++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_track(bool debug_eq, const float2 *win, const int *max_index, const float *max_value,
+                         const int *timing_cur, int *timing_next, sc_frame_result *results, long result_stride,
+                         float *eq_dbg, uint32_t call_index, unsigned long long keystream, int n_streams,
+                         cudaStream_t st) {
+    const int grid = (n_streams + TK_THREADS - 1) / TK_THREADS;
+    if (debug_eq)
+        track_kernel<true><<<grid, TK_THREADS, 0, st>>>(win, max_index, max_value, timing_cur, timing_next, results,
+                                                        result_stride, eq_dbg, call_index, keystream, n_streams);
+    else
+        track_kernel<false><<<grid, TK_THREADS, 0, st>>>(win, max_index, max_value, timing_cur, timing_next, results,
+                                                         result_stride, eq_dbg, call_index, keystream, n_streams);
+    g_launch_count++;
+    return cudaGetLastError();
+}
+
+}  // namespace sc
