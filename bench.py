@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- demodulated Msym/s of the batched RX chain on B200 (BASELINE.json metric).
+
+A "step" is one cold-start pass of the RX hot path (N lock-step copies of the reference's
+``while(1){fread; qpsk_rx_frame()}`` loop, /root/reference/src/qpsk.c:436-458) over one batch of
+synthetic streams.  Workload at every N: BASELINE.json configs[3]'s per-GPU shard -- 131,072
+streams per GPU (1M streams on 8 GPUs), 10 s = 80,000 samples = 42 calls each, weak scaling.
+Input is synthesised on the device by the library's own TX + channel kernels (reference packet
+structure, random frequency/phase offset, AWGN at Eb/N0 0..12 dB), 21 GB per GPU, so every step
+streams far more than the 126 MB L2.
+
+  value     whole-job Msym/s with the int16 samples already resident in HBM (CUDA events, max over ranks)
+  e2e       the same metric through the host-buffer entry point (sc_rx_frames_host): pinned host samples
+            -> H2D -> kernels -> D2H results, all inside the timed region
+  roofline  the dominant kernel's algorithmic bytes / its average launch duration, measured live with
+            CUDA events on the launching stream (single slab, so launches do not overlap)
+  cpu_baseline  the reference's own C objects (oracle/_ref) -- or the oracle port when absent -- timed on
+            this box's host cores on a bounded sample of the same input (rank 0, N=1 only)
+
+``--impl reference`` times only that CPU implementation (all host threads) and prints the same line
+with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAME = 1880
+SYM_PER_FRAME = 376
+METRIC = "demodulated_msym_per_s"
+UNIT = "Msym/s"
+
+# algorithmic bytes / FP32 operations per stream-frame
+FE_BYTES = 1494 * 2 + 198 * 8 + 8          # int16 samples the 290 decimated outputs depend on + tracker window + (idx,val)
+TK_BYTES = 198 * 8 + 12 + 32 + 4           # tracker window + (idx,val,timing) + result record + timing
+CHAIN_BYTES = 1880 * 2 + 32                # int16 frame in + result record out
+FE_OPS = 2 * 1494 + 290 * 198 + 2 * 255 + 128 * 128 * 2 + 128 * 3
+TK_OPS = 128 * 398 + 31 * 397
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        busy = sorted(sm)[len(sm) // 2:] if sm else []       # upper half = samples under load
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_input(sc, torch, bank, streams, samples_per_stream, seed, rank):
+    """Device-side synthesis of the step's input: reference packet structure + channel."""
+    dev = torch.device("cuda", bank.device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed + 7919 * rank)
+    period = FRAME + 903
+    n_packets = (samples_per_stream + period - 1) // period + 1
+    lead = torch.randint(0, period, (streams,), generator=g, device=dev, dtype=torch.int32)
+    df = (torch.rand(streams, generator=g, device=dev) * 40.0 - 20.0).float()
+    phi = (torch.rand(streams, generator=g, device=dev) * (2 * np.pi)).float()
+    ebn0_db = (torch.arange(streams, device=dev) % 13).float()            # 0..12 dB
+    # real AWGN: sigma^2 = P_sig * Fs / (2 * Rs * Es/N0), Es/N0 = 2 Eb/N0; P_sig of the data section
+    p_sig = 0.5 * (16384.0 * 0.48) ** 2 * 2.0
+    esn0 = 2.0 * 10.0 ** (ebn0_db / 10.0)
+    sigma = torch.sqrt(torch.tensor(p_sig, device=dev) * 8000.0 / (2.0 * 1600.0 * esn0)).float()
+    out = torch.empty((streams, samples_per_stream), dtype=torch.int16, device=dev)
+    bank.tx_packets_dev(out, n_packets, gap_samples=903, seed=seed + rank, lead_in=lead,
+                        channel={"df_hz": df, "phi_rad": phi, "sigma_lsb": sigma})
+    torch.cuda.synchronize(dev)
+    return out
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU implementation on this box's host cores."""
+    if rank != 0:
+        return
+    from oracle import cpu_bench
+    n_frames = args.seconds * 8000 // FRAME
+    streams = args.ref_streams
+    path = os.path.join(tempfile.gettempdir(), f"sc_ref_sample_{os.getpid()}.npy")
+    sample = None
+    try:
+        import torch
+        if torch.cuda.is_available():
+            import singlecarrier_b200 as sc
+            bank = sc.ModemBank(streams, device=0)
+            sample = synth_input(sc, torch, bank, streams, args.seconds * 8000, args.seed, 0).cpu().numpy()
+            bank.close()
+    except Exception as e:                                       # no GPU: CPU-synthesised packets, clean channel
+        print(f"[bench] reference arm: device synthesis unavailable ({e}); using oracle TX", file=sys.stderr)
+    if sample is None:
+        from oracle import pyoracle as po
+        from tests.helpers import synth_streams
+        sample = synth_streams(po.Oracle(), np.random.default_rng(args.seed), streams, n_frames)
+    np.save(path, sample)
+    r = cpu_bench.run(path, n_frames, None, args.warmup + args.steps)
+    os.unlink(path)
+    walls = r["wall_s"][args.warmup:]
+    total_sym = r["streams"] * n_frames * SYM_PER_FRAME * len(walls)
+    value = total_sym / sum(walls) / 1e6
+    sample_desc = f"{r['streams']} streams x {n_frames} calls of the same synthetic input per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(walls) / len(walls),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, streams_override=r["streams"]),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample_desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, streams_override=None):
+    return {
+        "workload": "BASELINE.json configs[3] per-GPU shard: 131072 streams/GPU x 10 s (1M streams on 8 GPUs), "
+                    "reference packets (640 preamble + 8x155 data + 903 dead air), df~U(-20,20) Hz, random phase, "
+                    "AWGN Eb/N0 0..12 dB",
+        "streams_per_gpu": streams_override if streams_override is not None else args.streams,
+        "seconds_per_stream": args.seconds, "calls_per_stream": args.seconds * 8000 // FRAME,
+        "samples_per_stream": args.seconds * 8000, "l2": "input per step (>= 2.6 GB at defaults) >> 126 MB L2; no flush needed",
+        "filter": "alpha=0.35 (firwide=false)", "parallelism": "streams sharded by rank, no hot-path collective",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=131072, help="streams per GPU")
+    ap.add_argument("--seconds", type=int, default=10, help="seconds of 8 kHz audio per stream")
+    ap.add_argument("--seed", type=int, default=0x5C0DE5)
+    ap.add_argument("--ref-streams", type=int, default=4096, help="streams per step of the CPU reference arm")
+    ap.add_argument("--cpu-streams", type=int, default=2048, help="streams of the cpu_baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import singlecarrier_b200 as sc
+    from singlecarrier_b200.modem import OPT_PROFILE, OPT_SLAB_PARTS
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; singlecarrier_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    streams, spp = args.streams, args.seconds * 8000
+    n_frames = spp // FRAME
+    bank = sc.ModemBank(streams, device=local_rank)
+    d_in = synth_input(sc, torch, bank, streams, spp, args.seed, rank)
+    d_res = torch.empty((streams, n_frames * 32), dtype=torch.uint8, device=dev)
+    counters = torch.zeros(16, dtype=torch.int64, device=dev)
+    stream_handle = torch.cuda.current_stream(dev).cuda_stream
+
+    def step():
+        bank.reset()
+        bank.rx_frames_dev(d_in, n_frames, d_res, stream=stream_handle)
+        counters.zero_()
+        bank.lock_stats(d_res, n_frames, counters, stream=stream_handle)
+        if world > 1:
+            dist.all_reduce(counters)                      # the only collective: lock / bit statistics
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = sc.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = sc.launch_count() - launches0
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    sym_per_step = world * streams * n_frames * SYM_PER_FRAME
+    value = sym_per_step * args.steps / (ms_total * 1e-3) / 1e6
+    stats = counters.cpu().numpy().tolist()
+
+    # ---- roofline: per-kernel durations with events on the launching stream, one slab ----------------
+    hbm_peak, sm_max, peak_src = peaks()
+    bank.set_option(OPT_SLAB_PARTS, 1)
+    bank.set_option(OPT_PROFILE, 1)
+    bank.reset()
+    bank.rx_frames_dev(d_in, n_frames, d_res, stream=stream_handle)
+    prof = bank.profile_read()
+    bank.set_option(OPT_PROFILE, 0)
+    bank.set_option(OPT_SLAB_PARTS, 0)
+    fe_ms = prof["frontend_ms"] / max(prof["frontend_launches"], 1)
+    tk_ms = prof["track_ms"] / max(prof["track_launches"], 1)
+    clk = (clocks.get("sm_mhz") or sm_max) * 1e6
+    fp32_peak = 148 * 128 * clk
+
+    def roof(name, ms_launch, bytes_sf, ops_sf):
+        gbs = streams * bytes_sf / (ms_launch * 1e-3) / 1e9
+        ops = streams * ops_sf / (ms_launch * 1e-3)
+        return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                "traffic": None, "ms_per_launch": ms_launch, "bytes_per_stream_frame": bytes_sf,
+                "fp32_issue": {"achieved_tops": ops / 1e12, "peak_tops": fp32_peak / 1e12, "frac": ops / fp32_peak,
+                               "ops_per_stream_frame": ops_sf, "note": "exact-order FP32 (no FMA): the true bound, SURVEY F8"}}
+
+    fe, tk = roof("frontend_kernel", fe_ms, FE_BYTES, FE_OPS), roof("track_kernel", tk_ms, TK_BYTES, TK_OPS)
+    dom, other = (tk, fe) if tk_ms >= fe_ms else (fe, tk)
+    roofline = dict(dom)
+    roofline["peak_source"] = peak_src
+    roofline["other_kernel"] = other
+    chain_gbs = streams * n_frames * CHAIN_BYTES * args.steps / (ms_total * 1e-3) / 1e9
+    roofline["chain"] = {"bytes_per_symbol": CHAIN_BYTES / SYM_PER_FRAME, "achieved_gbs": chain_gbs,
+                         "frac_of_hbm": chain_gbs / hbm_peak,
+                         "ops_per_symbol": (FE_OPS + TK_OPS) / SYM_PER_FRAME,
+                         "fp32_issue_frac": (value / world) * 1e6 * (FE_OPS + TK_OPS) / SYM_PER_FRAME / fp32_peak}
+
+    # ---- e2e: host buffers through sc_rx_frames_host ----------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, sc, torch, dist, bank, d_in, streams, n_frames, world, rank, dev, barrier)
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1) --------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = run_cpu_baseline(args, d_in, n_frames)
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "wall_ms_per_step": 1e3 * wall / args.steps,
+            "realtime_factor": value * 1e6 / (world * streams * 1600.0),
+            "lock_stats": {"calls": stats[0], "valid": stats[1], "sum_matches": stats[2], "bit_popcount": stats[5],
+                           "bit_checksum": stats[6]},
+        }
+        print(json.dumps(line), flush=True)
+    bank.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, sc, torch, dist, bank, d_in, streams, n_frames, world, rank, dev, barrier):
+    """Host-buffer path: pinned int16 samples in, results out, copies inside the timed region."""
+    import psutil
+    bytes_full = streams * n_frames * FRAME * 2
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    budget = psutil.virtual_memory().available * 0.6 / max(local_world, 1)
+    e_streams = streams
+    while e_streams * n_frames * FRAME * 2 > budget and e_streams > 1024:
+        e_streams //= 2
+    if world > 1:                                            # same size on every rank
+        t = torch.tensor([e_streams], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        e_streams = int(t.item())
+    h_in = torch.empty((e_streams, n_frames * FRAME), dtype=torch.int16, pin_memory=True)
+    h_in.copy_(d_in[:e_streams, : n_frames * FRAME])
+    h_res = torch.empty((e_streams, n_frames * 32), dtype=torch.uint8, pin_memory=True)
+    ebank = bank if e_streams == streams else sc.ModemBank(e_streams, device=bank.device)
+    x = h_in.numpy()
+    r = h_res.numpy().view(sc.RESULT_DTYPE)
+    steps = max(1, min(args.steps, 5))
+
+    def step():
+        ebank.reset()
+        ebank.rx_frames_host(x, n_frames, results=r)
+
+    step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    val = world * e_streams * n_frames * SYM_PER_FRAME * steps / dt / 1e6
+    valid = int(r["valid"].sum())
+    if ebank is not bank:
+        ebank.close()
+    return {"value": val, "unit": UNIT, "h2d_bytes_per_step": int(e_streams * n_frames * FRAME * 2),
+            "d2h_bytes_per_step": int(e_streams * n_frames * 32), "steps": steps, "streams_per_gpu": e_streams,
+            "ms_per_step": 1e3 * dt / steps, "api": "sc_rx_frames_host (pinned host int16 in, sc_frame_result out)",
+            "timer": "host wall clock around the blocking call, max over ranks", "valid_calls_last_step": valid,
+            "pcie_gbs": e_streams * n_frames * FRAME * 2 * steps / dt / 1e9}
+
+
+def run_cpu_baseline(args, d_in, n_frames):
+    ns = min(args.cpu_streams, d_in.shape[0])
+    path = os.path.join(tempfile.gettempdir(), f"sc_cpu_sample_{os.getpid()}.npy")
+    np.save(path, d_in[:ns, : n_frames * FRAME].cpu().numpy())
+    try:
+        out = subprocess.run([sys.executable, "-m", "oracle.cpu_bench", path, str(n_frames), "0", "1"],
+                             cwd=ROOT, capture_output=True, text=True, timeout=600)
+        r = json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        return {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {e}"}
+    finally:
+        if os.path.exists(path):
+            os.unlink(path)
+    return {"value": r["msym_per_s"][0], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+            "sample": f"first {r['streams']} streams x {n_frames} calls of rank 0's input "
+                      f"({r['streams'] * n_frames} qpsk_rx_frame calls, {r['wall_s'][0]:.2f} s wall, one process per core)",
+            "per_core": r["msym_per_s"][0] / r["cores"]}
+
+
+if __name__ == "__main__":
+    main()

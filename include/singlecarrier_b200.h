@@ -82,6 +82,16 @@ int  sc_device_count(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 uint64_t sc_launch_count(void);
 
+/* Options.  SC_OPT_SLAB_PARTS: split the bank into this many slabs of streams, issued round-robin
+ * on the library's internal CUDA streams (0 = default).  SC_OPT_PROFILE: bracket every front-end
+ * and tracking kernel launch with CUDA events on the stream it is launched on; sc_profile_read()
+ * synchronizes and returns {front-end ms, front-end launches, tracking ms, tracking launches}
+ * accumulated since the last read (use with SC_OPT_SLAB_PARTS = 1 so launches do not overlap). */
+#define SC_OPT_SLAB_PARTS 1
+#define SC_OPT_PROFILE    2
+int  sc_set_option(sc_modem *m, int option, int64_t value);
+int  sc_profile_read(sc_modem *m, double out[4]);
+
 /* ---- RX: replaces the while(1) loop of main() calling qpsk_rx_frame(), qpsk.c:436-458 --- */
 
 /*
@@ -173,6 +183,16 @@ int sc_track_decide_batch_dev(int device, int64_t n_streams, const float *symbol
  * 2..4096), out-of-place or in-place (in == out), unnormalised inverse like the reference. */
 int sc_fft_batch_dev(int device, int64_t n_batches, int nfft, int inverse, const float *in,
                      float *out, void *stream);
+
+/* ---- lock / bit statistics (reduced across GPUs with one ncclAllReduce) ----- */
+
+#define SC_N_COUNTERS 16
+/* counters (device pointer, uint64[16], ACCUMULATED into): 0 calls, 1 valid calls, 2 sum matches,
+ * 3 sum matches over valid calls, 4 sum max_index over valid calls, 5 popcount of bits over valid
+ * calls, 6 sum of (lo32(bits) + hi32(bits)) over valid calls (a checksum), 7 sum rx_timing,
+ * 8..15 histogram of matches in bins of 16.  All plain sums: ranks combine them by addition. */
+int sc_lock_stats_dev(int device, const sc_frame_result *results, int64_t n_streams, int64_t result_stride,
+                      int n_frames, uint64_t *counters, void *stream);
 
 /* ---- small utilities used by host code and tests --------------------------------------- */
 

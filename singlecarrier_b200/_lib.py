@@ -51,6 +51,8 @@ def _load() -> C.CDLL:
     sig("sc_version", C.c_char_p)
     sig("sc_device_count", i32)
     sig("sc_launch_count", u64)
+    sig("sc_set_option", i32, vp, i32, i64)
+    sig("sc_profile_read", i32, vp, C.POINTER(C.c_double))
     sig("sc_rx_frames_dev", i32, vp, vp, i64, i32, vp, i64, vp, vp)
     sig("sc_rx_frames_host", i32, vp, vp, i64, i32, vp, i64, vp)
     sig("sc_unpack_bits", None, vp, i64, vp)
@@ -60,6 +62,7 @@ def _load() -> C.CDLL:
     sig("sc_preamble_search_batch_dev", i32, i32, i64, vp, i64, vp, vp, vp)
     sig("sc_track_decide_batch_dev", i32, i32, i64, vp, i64, vp, vp, vp, u32, vp, vp, vp)
     sig("sc_fft_batch_dev", i32, i32, i64, i32, i32, vp, vp, vp)
+    sig("sc_lock_stats_dev", i32, i32, vp, i64, i64, i32, vp, vp)
     sig("sc_nco_table_host", i32, vp, i32, u32, i32, vp)
     sig("sc_keystream_word", u64, u32)
     return lib

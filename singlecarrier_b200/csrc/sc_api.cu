@@ -76,6 +76,11 @@ struct sc_modem {
     sc_frame_result *stage_res[N_PIPE] = {};
     float *stage_eq[N_PIPE] = {};
     size_t stage_in_cap = 0, stage_res_cap = 0, stage_eq_cap = 0;
+
+    // options / per-kernel profiling (bench.py's roofline leg)
+    int slab_parts = 0;                     // 0 = default (2 x N_PIPE slabs)
+    bool profile = false;
+    std::vector<cudaEvent_t> ev_fe, ev_tk;  // (start, stop) pairs
 };
 
 // ---- scrambler keystream (integer LFSR, src/scramble.c:57-69) ----------------------------------
@@ -245,6 +250,14 @@ static int prepare_tables(sc_modem *m, int n_frames, cudaStream_t st) {
     return SC_OK;
 }
 
+static cudaError_t prof_mark(std::vector<cudaEvent_t> &v, cudaStream_t st) {
+    cudaEvent_t e;
+    cudaError_t rc = cudaEventCreate(&e);
+    if (rc != cudaSuccess) return rc;
+    v.push_back(e);
+    return cudaEventRecord(e, st);
+}
+
 // One slab of streams [s0, s0+ns): the call loop.  `in` points at stream s0's first sample of the
 // first frame of this block, `results`/`eq_dbg` at stream s0's record of the block's first call.
 // call0 = index of the block's first call; kw = its keystream words; mix0 = table slot of frame
@@ -256,8 +269,10 @@ static int run_slab(sc_modem *m, cudaStream_t st, int64_t s0, int ns, const int1
     for (int j = 0; j < n_frames; j++) {
         const uint32_t n = call0 + (uint32_t) j;
         int *tc = m->timing[n & 1] + s0, *tn = m->timing[(n + 1) & 1] + s0;
+        if (m->profile) CU(prof_mark(m->ev_tk, st));
         CU(launch_track(m->debug_eq && eq_dbg != nullptr, win, m->max_index + s0, m->max_value + s0, tc, tn,
                         results + j, result_stride, eq_dbg ? eq_dbg + (size_t) j * 10 : nullptr, n, kw[j], ns, st));
+        if (m->profile) CU(prof_mark(m->ev_tk, st));
         if (n >= 1) {
             const int16_t *frame;
             int64_t fstride;
@@ -268,8 +283,10 @@ static int run_slab(sc_modem *m, cudaStream_t st, int64_t s0, int ns, const int1
                 frame = m->hist + (size_t) s0 * FRAME;
                 fstride = FRAME;
             }
+            if (m->profile) CU(prof_mark(m->ev_fe, st));
             CU(launch_frontend(m->wide, frame, fstride, mix0 + (size_t) j * FRAME, tc, tn, win, m->max_index + s0,
                                m->max_value + s0, ns, st));
+            if (m->profile) CU(prof_mark(m->ev_fe, st));
         }
     }
     if (save_hist && n_frames > 0) {
@@ -308,7 +325,7 @@ extern "C" int sc_rx_frames_dev(sc_modem *m, const int16_t *in, int64_t stream_s
     CU(cudaEventRecord(m->ev_start, m->pipe[0]));
     for (int i = 1; i < N_PIPE; i++) CU(cudaStreamWaitEvent(m->pipe[i], m->ev_start, 0));
 
-    const int64_t slab = pick_slab(m->n, 8192, 2 * N_PIPE);
+    const int64_t slab = pick_slab(m->n, m->slab_parts > 0 ? 128 : 8192, m->slab_parts > 0 ? m->slab_parts : 2 * N_PIPE);
     int k = 0;
     for (int64_t s0 = 0; s0 < m->n; s0 += slab, k++) {
         const int ns = (int) std::min<int64_t>(slab, m->n - s0);
@@ -356,7 +373,7 @@ extern "C" int sc_rx_frames_host(sc_modem *m, const int16_t *in, int64_t stream_
 
     // slabs of streams x blocks of frames; slab k always runs on pipe k % N_PIPE, so its blocks
     // stay in order and the staging buffer of that pipe is reused safely (stream order)
-    const int64_t slab = pick_slab(m->n, 4096, 2 * N_PIPE);
+    const int64_t slab = pick_slab(m->n, m->slab_parts > 0 ? 128 : 4096, m->slab_parts > 0 ? m->slab_parts : 2 * N_PIPE);
     const size_t frame_bytes = FRAME * sizeof(int16_t);
     int fblk = (int) std::max<int64_t>(1, std::min<int64_t>(n_frames, ((int64_t) 768 << 20) / (slab * (int64_t) frame_bytes)));
     int rc;
@@ -571,4 +588,55 @@ extern "C" int sc_fft_batch_dev(int device, int64_t n_batches, int nfft, int inv
     if (n_batches == 0) return SC_OK;
     CU(launch_fft_batch(n_batches, nfft, inverse, (const float2 *) in, (float2 *) out, (cudaStream_t) stream));
     return SC_OK;
+}
+
+extern "C" int sc_lock_stats_dev(int device, const sc_frame_result *results, int64_t n_streams, int64_t result_stride,
+                                 int n_frames, uint64_t *counters, void *stream) {
+    if (!results || !counters || n_streams < 0 || n_frames < 0 || result_stride < n_frames)
+        return fail(SC_EINVAL, "sc_lock_stats_dev: bad arguments");
+    int rc = stage_device(device);
+    if (rc != SC_OK) return rc;
+    if (n_streams == 0 || n_frames == 0) return SC_OK;
+    CU(launch_lock_stats(results, n_streams, result_stride, n_frames, (unsigned long long *) counters,
+                         (cudaStream_t) stream));
+    return SC_OK;
+}
+
+// ---- options and per-kernel profiling ----------------------------------------------------------
+extern "C" int sc_set_option(sc_modem *m, int option, int64_t value) {
+    if (!m) return fail(SC_EINVAL, "sc_set_option: null handle");
+    switch (option) {
+        case SC_OPT_SLAB_PARTS:
+            if (value < 0 || value > 1024) return fail(SC_EINVAL, "sc_set_option: slab parts out of range");
+            m->slab_parts = (int) value;
+            return SC_OK;
+        case SC_OPT_PROFILE:
+            m->profile = value != 0;
+            return SC_OK;
+        default:
+            return fail(SC_EINVAL, "sc_set_option: unknown option %d", option);
+    }
+}
+
+static int prof_sum(std::vector<cudaEvent_t> &v, double *ms, double *count) {
+    *ms = 0.0;
+    *count = 0.0;
+    for (size_t i = 0; i + 1 < v.size(); i += 2) {
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, v[i], v[i + 1]));
+        *ms += t;
+        *count += 1.0;
+    }
+    for (cudaEvent_t e : v) cudaEventDestroy(e);
+    v.clear();
+    return SC_OK;
+}
+
+extern "C" int sc_profile_read(sc_modem *m, double out[4]) {
+    if (!m || !out) return fail(SC_EINVAL, "sc_profile_read: bad arguments");
+    CU(cudaSetDevice(m->device));
+    CU(cudaDeviceSynchronize());
+    int rc = prof_sum(m->ev_fe, &out[0], &out[1]);
+    if (rc != SC_OK) return rc;
+    return prof_sum(m->ev_tk, &out[2], &out[3]);
 }

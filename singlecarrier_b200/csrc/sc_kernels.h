@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "../../include/singlecarrier_b200.h"
 
 namespace sc {
@@ -31,6 +33,10 @@ cudaError_t launch_track_window_batch(long n_streams, const float2 *symbols, lon
                                       sc_frame_result *results, float *eq_dbg, cudaStream_t st);
 cudaError_t launch_fft_batch(long n_batches, int nfft, int inverse, const float2 *in, float2 *out,
                              cudaStream_t st);
+
+// sc_stats_kernels.cu
+cudaError_t launch_lock_stats(const sc_frame_result *results, long n_streams, long result_stride, int n_frames,
+                              unsigned long long *counters, cudaStream_t st);
 
 // sc_tx_kernels.cu
 struct TxArgs {

@@ -18,6 +18,7 @@ FRAME_SIZE = 1880
 SYMBOLS_PER_FRAME = 376
 BITS_PER_CALL = 62
 PACKET_SAMPLES = 1880
+OPT_SLAB_PARTS, OPT_PROFILE = 1, 2
 REFERENCE_GAP = 903         # dead air between packets in the reference's main(), qpsk.c:410-412
 
 # sc_frame_result, include/singlecarrier_b200.h
@@ -83,6 +84,19 @@ class ModemBank:
     @property
     def call_index(self) -> int:
         return int(lib.sc_call_index(self._h))
+
+    def set_option(self, option: int, value: int) -> None:
+        check(lib.sc_set_option(self._h, option, value))
+
+    def profile_read(self) -> dict:
+        out = (C.c_double * 4)()
+        check(lib.sc_profile_read(self._h, out))
+        return {"frontend_ms": out[0], "frontend_launches": int(out[1]), "track_ms": out[2], "track_launches": int(out[3])}
+
+    def lock_stats(self, results, n_frames: int, counters, stream: int = 0) -> None:
+        """Accumulate the 16 lock/bit counters of results (CUDA uint8 [n, >= n_frames*32]) into counters (CUDA int64[16])."""
+        check(lib.sc_lock_stats_dev(self.device, results.data_ptr(), self.n_streams, results.stride(0) // 32, n_frames,
+                                    counters.data_ptr(), stream))
 
     # ---- RX ------------------------------------------------------------------------------------
     def rx_frames_host(self, samples: np.ndarray, n_frames: Optional[int] = None, results: Optional[np.ndarray] = None):
