@@ -192,11 +192,14 @@ def main():
     ap.add_argument("--seed", type=int, default=0x5C0DE5)
     ap.add_argument("--ref-streams", type=int, default=4096, help="streams per step of the CPU reference arm")
     ap.add_argument("--cpu-streams", type=int, default=2048, help="streams of the cpu_baseline sample")
+    ap.add_argument("--slab-parts", type=int, default=0, help="override the library's slab split (0 = default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
+    if args.slab_parts > 0:
+        os.environ["SC_SLAB_PARTS"] = str(args.slab_parts)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -272,7 +275,7 @@ def main():
     bank.rx_frames_dev(d_in, n_frames, d_res, stream=stream_handle)
     prof = bank.profile_read()
     bank.set_option(OPT_PROFILE, 0)
-    bank.set_option(OPT_SLAB_PARTS, 0)
+    bank.set_option(OPT_SLAB_PARTS, args.slab_parts)
     fe_ms = prof["frontend_ms"] / max(prof["frontend_launches"], 1)
     tk_ms = prof["track_ms"] / max(prof["track_launches"], 1)
     clk = (clocks.get("sm_mhz") or sm_max) * 1e6

@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -160,6 +161,7 @@ extern "C" int sc_create(sc_modem **out, int device, int64_t n_streams, uint32_t
     m->wide = (flags & SC_FLAG_WIDE) != 0;
     m->debug_eq = (flags & SC_FLAG_DEBUG_EQ) != 0;
     m->foffset = foffset_hz;
+    if (const char *e = getenv("SC_SLAB_PARTS")) m->slab_parts = atoi(e);
     m->rx_rect = nco_rect(-1100.0f + foffset_hz);                       // qpsk.c:428
     m->tx_rect = nco_rect(1100.0f);                                     // qpsk.c:376
     int rc = SC_OK;
@@ -325,7 +327,8 @@ extern "C" int sc_rx_frames_dev(sc_modem *m, const int16_t *in, int64_t stream_s
     CU(cudaEventRecord(m->ev_start, m->pipe[0]));
     for (int i = 1; i < N_PIPE; i++) CU(cudaStreamWaitEvent(m->pipe[i], m->ev_start, 0));
 
-    const int64_t slab = pick_slab(m->n, m->slab_parts > 0 ? 128 : 8192, m->slab_parts > 0 ? m->slab_parts : 2 * N_PIPE);
+    // default: two slabs, each on its own stream, so one slab's tail waves overlap the other's kernels
+    const int64_t slab = pick_slab(m->n, m->slab_parts > 0 ? 128 : 8192, m->slab_parts > 0 ? m->slab_parts : 2);
     int k = 0;
     for (int64_t s0 = 0; s0 < m->n; s0 += slab, k++) {
         const int ns = (int) std::min<int64_t>(slab, m->n - s0);

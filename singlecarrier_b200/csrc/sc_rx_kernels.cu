@@ -50,27 +50,89 @@ __global__ void nco_table_kernel(float2 *__restrict__ phase_state, float2 rect, 
 // inputs, so any output can be evaluated on its own, bit-exactly).  For i < 290 that is the sample
 // range [T-48, T+1445] of ONE frame (T >= 128 after the first call), 1494 samples.
 //
-// Shared memory per warp: the mixed samples as float2 with one pad slot every 50 samples
-// (pos = rel + rel/50), so that lane l, which evaluates outputs 10l..10l+9 and therefore reads
-// samples 50l .. 50l+93, has a lane stride of 51 slots (odd => conflict free 64-bit reads) and
-// compile-time offsets.  The region is then reused for W[290] and the (d,e) search operands.
+// The 290 outputs are produced in two passes of 145 (29 lanes x 5 consecutive outputs), so only
+// 769 mixed samples (6 KB) are staged in shared memory at a time: 25 KB per 4-warp CTA, 8 CTAs
+// = 32 warps per SM, which is what hides the latencies of the staging and epilogue phases behind
+// other warps' FIR/search arithmetic.  Lane l reads samples 25l .. 25l+68 of the pass: lane stride
+// 25 slots (odd => conflict-free 64-bit reads), compile-time offsets, taps as immediates.
+// All global loads of a stream-frame (24 coalesced 4-byte loads per lane) are issued up front.
 // ------------------------------------------------------------------------------------------------
 constexpr int FE_WARPS = 4;
-constexpr int FE_NSAMP = NTAPS + CYC * (WIN - 1);          // 1494
-constexpr int FE_MIX_SLOTS = FE_NSAMP + FE_NSAMP / 50 + 2; // 1525 (+ spare)
-constexpr int FE_OUT_PER_LANE = 10;
-constexpr int FE_FIR_LANES = WIN / FE_OUT_PER_LANE;        // 29
+constexpr int FE_NSAMP = NTAPS + CYC * (WIN - 1);           // 1494
+constexpr int FE_R = 5;                                     // outputs per lane per pass
+constexpr int FE_FIR_LANES = 29;
+constexpr int FE_PASS_OUT = FE_FIR_LANES * FE_R;            // 145
+constexpr int FE_PASS_SAMP = NTAPS + CYC * (FE_PASS_OUT - 1);   // 769
+constexpr int FE_FRONT = 2;                                 // slack slots in front (pair alignment)
+constexpr int FE_BUF = 784;                                 // FE_FRONT + 769 + pair slack, rounded
+constexpr int FE_NPAIR = (FE_NSAMP + 2 + 1) / 2;            // 748 int16 pairs cover any alignment
+constexpr int FE_PAIRS_PER_LANE = (FE_NPAIR + 31) / 32;     // 24
 constexpr int FE_DE_SLOTS = 320;                            // pos(x) = x + x/4, x < 255
-static_assert(WIN == FE_FIR_LANES * FE_OUT_PER_LANE, "290 = 29 x 10");
-static_assert(290 + FE_DE_SLOTS <= FE_MIX_SLOTS, "W and (d,e) reuse the mixed-sample region");
+static_assert(WIN == 2 * FE_PASS_OUT, "290 = 2 x 145");
+static_assert(WIN + FE_DE_SLOTS <= FE_BUF, "W and (d,e) reuse the mixed-sample region");
+static_assert(FE_FRONT + FE_PASS_SAMP + 2 <= FE_BUF, "pass buffer");
+
+// Stage the mixed samples rel in [h0, h0 + 769) of the stream-frame into buf (slot FE_FRONT + rel - h0).
+// Pair p holds samples rel = 2p - shift and 2p + 1 - shift; out-of-range slots land in the slack.
+constexpr int FE_KA_LO = 0, FE_KA_HI = 12;                  // pair rounds of pass A (rel 0..768)
+constexpr int FE_KB_LO = 11, FE_KB_HI = FE_PAIRS_PER_LANE - 1;   // pair rounds of pass B (rel 725..1493)
+constexpr int FE_KN = 13;
+static_assert(FE_KA_HI - FE_KA_LO + 1 == FE_KN && FE_KB_HI - FE_KB_LO + 1 == FE_KN, "13 rounds per pass");
+
+template <int K_LO>
+__device__ __forceinline__ void fe_load(uint32_t (&raw)[FE_KN], const uint32_t *__restrict__ fp, int lane, int base2) {
+#pragma unroll
+    for (int k = 0; k < FE_KN; k++) {
+        const int p = lane + 32 * (k + K_LO);
+        raw[k] = 0u;
+        if (p < FE_NPAIR && base2 + 2 * p + 1 < FRAME) raw[k] = __ldg(fp + p);
+    }
+}
+
+template <int K_LO>
+__device__ __forceinline__ void fe_stage(float2 *__restrict__ buf, const uint32_t (&rawk)[FE_KN],
+                                         const float2 *__restrict__ tab, int lane, int shift, int h0) {
+#pragma unroll
+    for (int kk = 0; kk < FE_KN; kk++) {
+        const int k = kk + K_LO;
+        const uint32_t (&raw)[FE_KN] = rawk;
+        const int p = lane + 32 * k;
+        const int d = FE_FRONT + 2 * p - shift - h0;          // slot of the pair's first sample
+        if (d >= 0 && d + 1 < FE_BUF && p < FE_NPAIR) {
+            const float4 ph = __ldg(reinterpret_cast<const float4 *>(tab + 2 * p));
+            const float v0 = (float) (int16_t) (raw[kk] & 0xffffu);
+            const float v1 = (float) (int16_t) (raw[kk] >> 16);
+            buf[d] = make_float2(__fmul_rn(ph.x, v0), __fmul_rn(ph.y, v0));       // qpsk.c:141
+            buf[d + 1] = make_float2(__fmul_rn(ph.z, v1), __fmul_rn(ph.w, v1));
+        }
+    }
+}
+
+// 49-tap RRC at 5 consecutive decimated instants per lane (src/fir.c:36-42): y += mem[i]*coeff[i]
+// left to right, both components at once (packed f32x2, see sc_exact.cuh).
+template <bool WIDE>
+__device__ __forceinline__ void fe_fir(const float2 *__restrict__ buf, int lane, u64 (&acc)[FE_R]) {
+#pragma unroll
+    for (int r = 0; r < FE_R; r++) acc[r] = 0ull;
+    const u64 *mp = reinterpret_cast<const u64 *>(buf) + FE_FRONT + CYC * FE_R * lane;
+#pragma unroll
+    for (int j = 0; j < NTAPS + CYC * (FE_R - 1); j++) {
+        const u64 x = mp[j];
+#pragma unroll
+        for (int r = 0; r < FE_R; r++) {
+            const int k = j - CYC * r;
+            if (k >= 0 && k < NTAPS) acc[r] = pk_add(acc[r], pk_mul_bcast_pz(x, tap<WIDE>(k)));
+        }
+    }
+}
 
 template <bool WIDE>
-__global__ void __launch_bounds__(FE_WARPS * 32)
+__global__ void __launch_bounds__(FE_WARPS * 32, 8)
 frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2 *__restrict__ mix_table,
                 const int *__restrict__ timing_cur, const int *__restrict__ timing_next,
                 float2 *__restrict__ win, int *__restrict__ max_index_out, float *__restrict__ max_value_out,
                 int n_streams) {
-    __shared__ __align__(16) float2 smem[FE_WARPS][FE_MIX_SLOTS];
+    __shared__ __align__(16) float2 smem[FE_WARPS][FE_BUF];
     __shared__ int s_maxidx[FE_WARPS];
     __shared__ int s_t2[FE_WARPS];
 
@@ -79,75 +141,84 @@ frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2
     const bool active = s < n_streams;
     float2 *mix = smem[warp];
 
+    u64 accA[FE_R], accB[FE_R];
+#pragma unroll
+    for (int r = 0; r < FE_R; r++) accA[r] = accB[r] = 0ull;
+
+    // warp-uniform set-up
+    int base = 0, shift = 0, base2 = 0;
+    bool fast = false;
+    const int16_t *frame = in;
+    const float2 *tab = mix_table;
+    const uint32_t *fp = nullptr;
+    uint32_t raw[FE_KN];
+#pragma unroll
+    for (int k = 0; k < FE_KN; k++) raw[k] = 0u;
     if (active) {
         const int T = timing_cur[s];
-        const int base = T - (NTAPS - 1);              // first sample needed (may be < 0 only if T < 48)
-        const int16_t *frame = in + s * stream_stride;
-
-        // ---- stage 1: load int16, mix to baseband, stage in shared memory (qpsk.c:138-145) ----
-        if ((((uintptr_t) frame) & 15) == 0) {
-            const int c0 = (base < 0 ? 0 : base) >> 3;
-            const int c1 = (base + FE_NSAMP - 1) >> 3;
-            for (int c = c0 + lane; c <= c1; c += 32) {
-                const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(frame) + c);
-                const float4 *tp = reinterpret_cast<const float4 *>(mix_table + c * 8);
-                const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-                const int rel0 = c * 8 - base;
-#pragma unroll
-                for (int h = 0; h < 4; h++) {
-                    const float4 ph = __ldg(tp + h);
-                    const float v0 = (float) (int16_t) (w[h] & 0xffffu);
-                    const float v1 = (float) (int16_t) (w[h] >> 16);
-                    const int r0 = rel0 + 2 * h, r1 = r0 + 1;
-                    if (r0 >= 0 && r0 < FE_NSAMP)
-                        mix[r0 + r0 / 50] = make_float2(__fmul_rn(ph.x, v0), __fmul_rn(ph.y, v0));
-                    if (r1 >= 0 && r1 < FE_NSAMP)
-                        mix[r1 + r1 / 50] = make_float2(__fmul_rn(ph.z, v1), __fmul_rn(ph.w, v1));
-                }
-            }
-        } else {
-            for (int rel = lane; rel < FE_NSAMP; rel += 32) {
-                const int t = base + rel;
-                if (t >= 0) {
-                    const float v = (float) frame[t];
-                    const float2 ph = __ldg(mix_table + t);
-                    mix[rel + rel / 50] = make_float2(__fmul_rn(ph.x, v), __fmul_rn(ph.y, v));
-                }
-            }
-        }
-        if (base < 0) {   // cold-start timing only: samples before the frame are taken as silence
-            for (int rel = lane; rel < -base && rel < FE_NSAMP; rel += 32) mix[rel + rel / 50] = make_float2(0.f, 0.f);
+        base = T - (NTAPS - 1);                        // first sample needed; >= 80 once T >= 128
+        frame = in + s * stream_stride;
+        fast = base >= 0 && ((((uintptr_t) frame) & 3) == 0);
+        if (fast) {
+            // ---- stage 1: pass A's global loads (coalesced 4-byte loads, the kernel's only HBM reads) ----
+            base2 = base & ~1;
+            shift = base - base2;
+            fp = reinterpret_cast<const uint32_t *>(frame + base2);
+            tab = mix_table + base2;
+            fe_load<FE_KA_LO>(raw, fp, lane, base2);
         }
     }
-    __syncwarp();
 
-    // ---- stage 2: 49-tap RRC at 10 consecutive decimated instants per lane (src/fir.c:36-42) ----
-    u64 acc[FE_OUT_PER_LANE];
-#pragma unroll
-    for (int r = 0; r < FE_OUT_PER_LANE; r++) acc[r] = 0ull;
-
-    if (active && lane < FE_FIR_LANES) {
-        const u64 *mp = reinterpret_cast<const u64 *>(mix) + 51 * lane;
-#pragma unroll
-        for (int j = 0; j < NTAPS + CYC * (FE_OUT_PER_LANE - 1); j++) {
-            const u64 x = mp[j + (j >= 50 ? 1 : 0)];
-#pragma unroll
-            for (int r = 0; r < FE_OUT_PER_LANE; r++) {
-                const int k = j - CYC * r;
-                if (k >= 0 && k < NTAPS) acc[r] = pk_add(acc[r], pk_mul_bcast_pz(x, tap<WIDE>(k)));
+    // ---- two passes: A = outputs 0..144 (rel 0..768), B = outputs 145..289 (rel 725..1493)
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+        const int h0 = h * CYC * FE_PASS_OUT;
+        if (active) {
+            if (fast) {
+                if (h == 0) {
+                    fe_stage<FE_KA_LO>(mix, raw, tab, lane, shift, 0);
+                    fe_load<FE_KB_LO>(raw, fp, lane, base2);       // pass B's loads fly during pass A's FIR
+                } else {
+                    fe_stage<FE_KB_LO>(mix, raw, tab, lane, shift, CYC * FE_PASS_OUT);
+                }
+            } else {
+                // generic path (odd byte alignment, or the cold-start timing T < 48 where samples
+                // before the frame are silence): same arithmetic, scalar loads
+                for (int rel = lane; rel < FE_PASS_SAMP; rel += 32) {
+                    const int t = base + h0 + rel;
+                    float2 v = make_float2(0.f, 0.f);
+                    if (t >= 0) {
+                        const float x = (float) frame[t];
+                        const float2 ph = __ldg(mix_table + t);
+                        v = make_float2(__fmul_rn(ph.x, x), __fmul_rn(ph.y, x));
+                    }
+                    mix[FE_FRONT + rel] = v;
+                }
             }
         }
+        __syncwarp();
+        u64 acc[FE_R];
+#pragma unroll
+        for (int r = 0; r < FE_R; r++) acc[r] = 0ull;
+        if (active && lane < FE_FIR_LANES) fe_fir<WIDE>(mix, lane, acc);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < FE_R; r++) {
+            if (h == 0) accA[r] = acc[r];
+            else accB[r] = acc[r];
+        }
     }
-    __syncwarp();
 
     float2 *W = mix;                       // [290]
     float2 *DE = mix + WIN;                // [320], pos(x) = x + x/4
     if (active && lane < FE_FIR_LANES) {
 #pragma unroll
-        for (int r = 0; r < FE_OUT_PER_LANE; r++) {
+        for (int r = 0; r < FE_R; r++) {
             float yr, yi;
-            unpk(acc[r], yr, yi);
-            W[FE_OUT_PER_LANE * lane + r] = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));
+            unpk(accA[r], yr, yi);
+            W[FE_R * lane + r] = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));    // src/fir.c:42
+            unpk(accB[r], yr, yi);
+            W[FE_PASS_OUT + FE_R * lane + r] = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));
         }
     }
     __syncwarp();
@@ -252,9 +323,11 @@ track_kernel(const float2 *__restrict__ win, const int *__restrict__ max_index, 
     // equalize(), qpsk.c:111-123, and magnitude(), qpsk.c:101-109, in one pass
     int matches = 0;
     float mag = 0.0f;
+    c32 nxt = from2(X[(EQ - 1) * 32]);             // one step ahead, so the load latency hides behind a step
 #pragma unroll 1
     for (int i = 0; i < PRE; i++) {
-        x[EQ - 1] = from2(X[(i + EQ - 1) * 32]);
+        x[EQ - 1] = nxt;
+        nxt = from2(X[(i + EQ) * 32]);
         const float ref = ((c_pre_neg[i >> 5] >> (i & 31)) & 1u) ? -1.0f : 1.0f;
         mag = __fadd_rn(mag, __fadd_rn(__fmul_rn(x[0].r, x[0].r), __fmul_rn(x[0].i, x[0].i)));
         const float er = tk.train(x, ref);
@@ -274,9 +347,11 @@ track_kernel(const float2 *__restrict__ win, const int *__restrict__ max_index, 
 
     unsigned long long word = 0ull;
     float cost = 0.0f;
+    nxt = from2(Dw[(EQ - 1) * 32]);
 #pragma unroll 1
     for (int i = 0; i < NDATA; i++) {
-        x[EQ - 1] = from2(Dw[(i + EQ - 1) * 32]);
+        x[EQ - 1] = nxt;
+        nxt = from2(Dw[min(i + EQ, Y_ROWS - 1) * 32]);
         int bI, bQ;
         const float er = tk.data(x, bI, bQ);
         cost = __fadd_rn(cost, er);                                // qpsk.c:228
