@@ -179,10 +179,15 @@ int sc_track_decide_batch_dev(int device, int64_t n_streams, const float *symbol
                               int32_t *rx_timing, uint32_t call_index, sc_frame_result *results,
                               float *eq_dbg, void *stream);
 
-/* fft(), fft.h:46: n_batches independent length-nfft complex FFTs (nfft a power of two,
- * 2..4096), out-of-place or in-place (in == out), unnormalised inverse like the reference. */
-int sc_fft_batch_dev(int device, int64_t n_batches, int nfft, int inverse, const float *in,
-                     float *out, void *stream);
+/* fft(), fft.h:46 / src/fft.c:133: n_batches independent length-nfft complex FFTs (any nfft the
+ * reference accepts: radix 4, 2, 3, 5 and generic stages), out of place, unnormalised inverse.
+ * Same factorisation, butterfly arithmetic and twiddles as src/fft.c. */
+int sc_fft_batch_dev(int device, int64_t n_batches, int nfft, int inverse, const float *in, float *out,
+                     void *stream);
+/* fftr()/fftri(), fft.h:51-52 (encode_fftr/encode_fftri in src/fft.c:139-186): real nfft (even)
+ * -> nfft/2+1 complex bins, and back (unnormalised). */
+int sc_fftr_batch_dev(int device, int64_t n_batches, int nfft, const float *in, float *out, void *stream);
+int sc_fftri_batch_dev(int device, int64_t n_batches, int nfft, const float *in, float *out, void *stream);
 
 /* ---- lock / bit statistics (reduced across GPUs with one ncclAllReduce) ----- */
 

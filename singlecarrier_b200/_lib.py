@@ -62,6 +62,8 @@ def _load() -> C.CDLL:
     sig("sc_preamble_search_batch_dev", i32, i32, i64, vp, i64, vp, vp, vp)
     sig("sc_track_decide_batch_dev", i32, i32, i64, vp, i64, vp, vp, vp, u32, vp, vp, vp)
     sig("sc_fft_batch_dev", i32, i32, i64, i32, i32, vp, vp, vp)
+    sig("sc_fftr_batch_dev", i32, i32, i64, i32, vp, vp, vp)
+    sig("sc_fftri_batch_dev", i32, i32, i64, i32, vp, vp, vp)
     sig("sc_lock_stats_dev", i32, i32, vp, i64, i64, i32, vp, vp)
     sig("sc_nco_table_host", i32, vp, i32, u32, i32, vp)
     sig("sc_keystream_word", u64, u32)

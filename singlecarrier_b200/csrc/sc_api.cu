@@ -11,6 +11,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <tuple>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -582,15 +584,113 @@ extern "C" int sc_track_decide_batch_dev(int device, int64_t n_streams, const fl
     return SC_OK;
 }
 
-extern "C" int sc_fft_batch_dev(int device, int64_t n_batches, int nfft, int inverse, const float *in, float *out,
-                                void *stream) {
-    if (n_batches < 0 || !in || !out || nfft < 2 || nfft > 4096 || (nfft & (nfft - 1)))
-        return fail(SC_EINVAL, "sc_fft_batch_dev: nfft must be a power of two in 2..4096");
+// ---- FFT (fft.h) --------------------------------------------------------------------------------
+// kf_factor(), src/fft.c:433-459: radix 4 first, then 2, 3, 5, 7, ...; p > floor(sqrt(n)) => p = n
+namespace sc {
+void fft_make_plan(int n, int inverse, FftPlan *plan) {
+    plan->n = n;
+    plan->inverse = inverse ? 1 : 0;
+    int p = 4, k = 0;
+    const float floor_sqrt = floorf(sqrtf((float) n));
+    do {
+        while (n % p) {
+            switch (p) {
+                case 4: p = 2; break;
+                case 2: p = 3; break;
+                default: p += 2;
+            }
+            if (p > floor_sqrt) p = n;
+        }
+        n /= p;
+        plan->p[k] = p;
+        plan->m[k] = n;
+        k++;
+    } while (n > 1);
+    plan->n_stages = k;
+}
+
+// twiddles exactly as fft_alloc() computes them (src/fft.c:70-77), same libm as the reference
+void fft_make_twiddles(int n, int inverse, float2 *tw) {
+    const double tau = 2.0f * M_PI;
+    for (int i = 0; i < n; i++) {
+        float phase = (float) (-tau * (float) i / (float) n);
+        if (inverse) phase *= -1.0f;
+        tw[i] = make_float2(cosf(phase), sinf(phase));
+    }
+}
+
+// super twiddles of fftr_alloc() (src/fft.c:118-126); ncfft = nfft/2
+void fft_make_super_twiddles(int ncfft, int inverse, float2 *tw) {
+    for (int i = 0; i < ncfft / 2; i++) {
+        float phase = (float) (-M_PI * ((float) (i + 1) / (float) ncfft + .5f));
+        if (inverse) phase *= -1.0f;
+        tw[i] = make_float2(cosf(phase), sinf(phase));
+    }
+}
+}  // namespace sc
+
+struct FftDeviceTables {
+    float2 *tw = nullptr, *super_tw = nullptr, *scratch = nullptr;
+};
+static std::mutex g_fft_mu;
+static std::map<std::tuple<int, int, int, int>, FftDeviceTables> g_fft_tables;   // (device, n, inverse, real)
+
+static int fft_tables(int device, int n, int inverse, bool real, FftDeviceTables *out) {
+    std::lock_guard<std::mutex> lock(g_fft_mu);
+    auto key = std::make_tuple(device, n, inverse ? 1 : 0, real ? 1 : 0);
+    auto it = g_fft_tables.find(key);
+    if (it != g_fft_tables.end()) {
+        *out = it->second;
+        return SC_OK;
+    }
+    FftDeviceTables t;
+    std::vector<float2> h(n);
+    fft_make_twiddles(n, inverse, h.data());
+    CU(cudaMalloc(&t.tw, (size_t) n * sizeof(float2)));
+    CU(cudaMemcpy(t.tw, h.data(), (size_t) n * sizeof(float2), cudaMemcpyHostToDevice));
+    if (real) {
+        std::vector<float2> hs(std::max(n / 2, 1));
+        fft_make_super_twiddles(n, inverse, hs.data());
+        CU(cudaMalloc(&t.super_tw, hs.size() * sizeof(float2)));
+        CU(cudaMemcpy(t.super_tw, hs.data(), hs.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    if ((size_t) 2 * n * sizeof(float2) > 64 * 1024)
+        CU(cudaMalloc(&t.scratch, (size_t) FFT_SCRATCH_CTAS * 2 * n * sizeof(float2)));
+    g_fft_tables[key] = t;
+    *out = t;
+    return SC_OK;
+}
+
+static int fft_run(int device, int64_t n_batches, int n_core, int inverse, int mode, const void *in, void *out,
+                   void *stream) {
     int rc = stage_device(device);
     if (rc != SC_OK) return rc;
     if (n_batches == 0) return SC_OK;
-    CU(launch_fft_batch(n_batches, nfft, inverse, (const float2 *) in, (float2 *) out, (cudaStream_t) stream));
+    FftDeviceTables t;
+    if ((rc = fft_tables(device, n_core, inverse, mode != 0, &t)) != SC_OK) return rc;
+    FftPlan plan;
+    fft_make_plan(n_core, inverse, &plan);
+    CU(launch_fft(plan, t.tw, t.super_tw, mode, in, out, t.scratch, n_batches, (cudaStream_t) stream));
     return SC_OK;
+}
+
+extern "C" int sc_fft_batch_dev(int device, int64_t n_batches, int nfft, int inverse, const float *in, float *out,
+                                void *stream) {
+    if (n_batches < 0 || !in || !out || nfft < 1 || nfft > (1 << 20))
+        return fail(SC_EINVAL, "sc_fft_batch_dev: bad arguments");
+    return fft_run(device, n_batches, nfft, inverse, 0, in, out, stream);
+}
+
+extern "C" int sc_fftr_batch_dev(int device, int64_t n_batches, int nfft, const float *in, float *out, void *stream) {
+    if (n_batches < 0 || !in || !out || nfft < 2 || (nfft & 1) || nfft > (1 << 21))
+        return fail(SC_EINVAL, "sc_fftr_batch_dev: nfft must be even");
+    return fft_run(device, n_batches, nfft / 2, 0, 1, in, out, stream);
+}
+
+extern "C" int sc_fftri_batch_dev(int device, int64_t n_batches, int nfft, const float *in, float *out, void *stream) {
+    if (n_batches < 0 || !in || !out || nfft < 2 || (nfft & 1) || nfft > (1 << 21))
+        return fail(SC_EINVAL, "sc_fftri_batch_dev: nfft must be even");
+    return fft_run(device, n_batches, nfft / 2, 1, 2, in, out, stream);
 }
 
 extern "C" int sc_lock_stats_dev(int device, const sc_frame_result *results, int64_t n_streams, int64_t result_stride,

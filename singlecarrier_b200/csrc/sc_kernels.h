@@ -31,8 +31,15 @@ cudaError_t launch_track_window_batch(long n_streams, const float2 *symbols, lon
                                       const int *max_index, const float *max_value, int *rx_timing,
                                       uint32_t call_index, unsigned long long keystream,
                                       sc_frame_result *results, float *eq_dbg, cudaStream_t st);
-cudaError_t launch_fft_batch(long n_batches, int nfft, int inverse, const float2 *in, float2 *out,
-                             cudaStream_t st);
+
+// sc_fft_kernels.cu
+struct FftPlan {
+    int n, inverse, n_stages;
+    int p[32], m[32];   // kf_factor(): radix and remaining length per stage (src/fft.c:433-459)
+};
+constexpr int FFT_SCRATCH_CTAS = 64;
+cudaError_t launch_fft(const FftPlan &plan, const float2 *tw, const float2 *super_tw, int mode, const void *in,
+                       void *out, float2 *scratch, long n_batches, cudaStream_t st);
 
 // sc_stats_kernels.cu
 cudaError_t launch_lock_stats(const sc_frame_result *results, long n_streams, long result_stride, int n_frames,

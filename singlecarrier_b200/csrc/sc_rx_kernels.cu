@@ -11,11 +11,12 @@
 #include "sc_common.cuh"
 #include "sc_tables.cuh"
 #include "sc_tracker.cuh"
+#include "sc_search.cuh"
+#include "sc_track_core.cuh"
 #include "sc_kernels.h"
 
 namespace sc {
 
-__constant__ uint32_t c_pre_neg[4] = {pre_neg_word(0), pre_neg_word(1), pre_neg_word(2), pre_neg_word(3)};
 
 // ------------------------------------------------------------------------------------------------
 // NCO phasor table.  The reference advances one complex phasor per sample by a float recurrence
@@ -67,7 +68,7 @@ constexpr int FE_FRONT = 2;                                 // slack slots in fr
 constexpr int FE_BUF = 784;                                 // FE_FRONT + 769 + pair slack, rounded
 constexpr int FE_NPAIR = (FE_NSAMP + 2 + 1) / 2;            // 748 int16 pairs cover any alignment
 constexpr int FE_PAIRS_PER_LANE = (FE_NPAIR + 31) / 32;     // 24
-constexpr int FE_DE_SLOTS = 320;                            // pos(x) = x + x/4, x < 255
+constexpr int FE_DE_SLOTS = SEARCH_DE_SLOTS;                 // pos(x) = x + x/4, x < 255
 static_assert(WIN == 2 * FE_PASS_OUT, "290 = 2 x 145");
 static_assert(WIN + FE_DE_SLOTS <= FE_BUF, "W and (d,e) reuse the mixed-sample region");
 static_assert(FE_FRONT + FE_PASS_SAMP + 2 <= FE_BUF, "pass buffer");
@@ -223,52 +224,16 @@ frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2
     }
     __syncwarp();
 
-    // ---- stage 3: preamble search (qpsk.c:88-96, 172-183) ----
-    // pre[i] = v(1+1i), v = +-1  =>  pre[i]*s = v*(s.r - s.i) + i*v*(s.i + s.r) exactly, so keep
-    // d = s.r - s.i, e = s.i + s.r once per symbol and accumulate +-(d,e) in the reference's order.
+    // ---- stage 3: preamble search (qpsk.c:88-96, 172-183), see sc_search.cuh ----
     if (active) {
-        for (int x = lane; x < 255; x += 32) {
-            const float2 w = W[x];
-            DE[x + (x >> 2)] = make_float2(__fsub_rn(w.x, w.y), __fadd_rn(w.y, w.x));
-        }
+        for (int x = lane; x < SEARCH_SYMS; x += 32) DE[de_pos(x)] = de_from_symbol(W[x]);
     }
     __syncwarp();
 
-    int best_idx = 0;
-    float best_val = 0.0f;
     if (active) {
-        u64 a[4] = {0ull, 0ull, 0ull, 0ull};
-        const u64 *dp = reinterpret_cast<const u64 *>(DE) + 5 * lane;     // lags 4*lane .. 4*lane+3
-#pragma unroll
-        for (int j = 0; j < PRE + 3; j++) {
-            const u64 v = dp[j + (j >> 2)];
-#pragma unroll
-            for (int qd = 0; qd < 4; qd++) {
-                const int i = j - qd;
-                if (i >= 0 && i < PRE) a[qd] = pre_neg(i) ? pk_sub(a[qd], v) : pk_add(a[qd], v);
-            }
-        }
-#pragma unroll
-        for (int qd = 0; qd < 4; qd++) {
-            float re, im;
-            unpk(a[qd], re, im);
-            const float val = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));   // cnormf, qpsk.c:75-80
-            if (val > best_val) {
-                best_val = val;
-                best_idx = 4 * lane + qd;
-            }
-        }
-        // strict '>' with first maximum winning == largest value, smallest lag among ties
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, best_val, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
-            if (ov > best_val || (ov == best_val && oi < best_idx)) {
-                best_val = ov;
-                best_idx = oi;
-            }
-        }
-        if (best_val == 0.0f) best_idx = 0;     // nothing ever exceeded the initial 0.0f
+        int best_idx;
+        float best_val;
+        search_warp(DE, lane, best_idx, best_val);
         if (lane == 0) {
             max_index_out[s] = best_idx;
             max_value_out[s] = best_val;
@@ -302,6 +267,12 @@ frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2
 // ------------------------------------------------------------------------------------------------
 constexpr int TK_THREADS = 128;
 
+struct TileLoader {
+    const float2 *X;      // this stream's column of its 32-stream tile
+    __device__ __forceinline__ c32 x(int r) const { return from2(X[r * 32]); }
+    __device__ __forceinline__ c32 y(int r) const { return from2(X[(X_ROWS + r) * 32]); }
+};
+
 template <bool DEBUG_EQ>
 __global__ void __launch_bounds__(TK_THREADS)
 track_kernel(const float2 *__restrict__ win, const int *__restrict__ max_index, const float *__restrict__ max_value,
@@ -311,80 +282,23 @@ track_kernel(const float2 *__restrict__ win, const int *__restrict__ max_index, 
     const long s = (long) blockIdx.x * TK_THREADS + threadIdx.x;
     if (s >= n_streams) return;
 
-    const float2 *X = win + ((s >> 5) * WIN_ROWS) * 32 + (s & 31);
+    TileLoader ld;
+    ld.X = win + ((s >> 5) * WIN_ROWS) * 32 + (s & 31);
+    TrackOut o;
+    track_core(ld, o);
 
-    Tracker tk;
-    tk.reset();                                                    // qpsk.c:186
-
-    c32 x[EQ];
-#pragma unroll
-    for (int i = 0; i < EQ - 1; i++) x[i] = from2(X[i * 32]);
-
-    // equalize(), qpsk.c:111-123, and magnitude(), qpsk.c:101-109, in one pass
-    int matches = 0;
-    float mag = 0.0f;
-    c32 nxt = from2(X[(EQ - 1) * 32]);             // one step ahead, so the load latency hides behind a step
-#pragma unroll 1
-    for (int i = 0; i < PRE; i++) {
-        x[EQ - 1] = nxt;
-        nxt = from2(X[(i + EQ) * 32]);
-        const float ref = ((c_pre_neg[i >> 5] >> (i & 31)) & 1u) ? -1.0f : 1.0f;
-        mag = __fadd_rn(mag, __fadd_rn(__fmul_rn(x[0].r, x[0].r), __fmul_rn(x[0].i, x[0].i)));
-        const float er = tk.train(x, ref);
-        if (__fmul_rn(er, ref) > 0.0f) matches++;
-#pragma unroll
-        for (int k = 0; k < EQ - 1; k++) x[k] = x[k + 1];
-    }
-
-    const bool valid = matches > MATCH_THRESHOLD;                  // qpsk.c:196
     const int t_in = timing_cur[s];
     const int mi = max_index[s];
-
-    // valid: data symbols follow the preamble (rows 128..); invalid: they start at rx_timing (rows 163..)
-    const float2 *Dw = valid ? X + PRE * 32 : X + X_ROWS * 32;
-#pragma unroll
-    for (int i = 0; i < EQ - 1; i++) x[i] = from2(Dw[i * 32]);
-
-    unsigned long long word = 0ull;
-    float cost = 0.0f;
-    nxt = from2(Dw[(EQ - 1) * 32]);
-#pragma unroll 1
-    for (int i = 0; i < NDATA; i++) {
-        x[EQ - 1] = nxt;
-        nxt = from2(Dw[min(i + EQ, Y_ROWS - 1) * 32]);
-        int bI, bQ;
-        const float er = tk.data(x, bI, bQ);
-        cost = __fadd_rn(cost, er);                                // qpsk.c:228
-        word |= ((unsigned long long) (unsigned) (bQ | (bI << 1))) << (2 * i);   // bits[2i]=Q, bits[2i+1]=I
-#pragma unroll
-        for (int k = 0; k < EQ - 1; k++) x[k] = x[k + 1];
-    }
-
-    const int t_out = valid ? mi + PRE : t_in;                     // qpsk.c:219
+    const int t_out = o.valid ? mi + PRE : t_in;                   // qpsk.c:219
     timing_next[s] = t_out;
-
-    sc_frame_result r;
-    r.bits = word ^ keystream;                                     // scramble(bits, rx), equalizer.c:87
-    r.max_value = max_value[s];
-    r.cost = valid ? mag : cost;
-    r.max_index = (int16_t) mi;
-    r.matches = (int16_t) matches;
-    r.rx_timing = (int16_t) t_out;
-    r.valid = valid ? 1 : 0;
-    r.reserved0 = 0;
-    r.call_index = call_index;
-    r.reserved1 = 0;
-    uint4 *dst = reinterpret_cast<uint4 *>(results + s * result_stride);
-    const uint4 *srcp = reinterpret_cast<const uint4 *>(&r);
-    dst[0] = srcp[0];
-    dst[1] = srcp[1];
+    store_result(results + s * result_stride, o, keystream, max_value[s], mi, t_out, call_index);
 
     if (DEBUG_EQ && eq_dbg != nullptr) {
         float *e = eq_dbg + s * result_stride * 10;
 #pragma unroll
         for (int i = 0; i < EQ; i++) {
-            e[2 * i] = tk.C[i].r;
-            e[2 * i + 1] = tk.C[i].i;
+            e[2 * i] = o.tk.C[i].r;
+            e[2 * i + 1] = o.tk.C[i].i;
         }
     }
 }

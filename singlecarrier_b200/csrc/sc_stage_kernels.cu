@@ -1,0 +1,165 @@
+// sc_stage_kernels.cu -- batched forms of the reference's L1 primitives as stand-alone kernels
+// (the stage entry points of include/singlecarrier_b200.h and the back end of the drop-in symbols).
+//   fir_batch_kernel     fir()                            src/fir.c:22-44
+//   search_batch_kernel  correlate() + argmax             src/qpsk.c:88-96, 172-183
+//   track_window_kernel  kalman_reset .. data_eq loop     src/qpsk.c:186-238
+#include "sc_common.cuh"
+#include "sc_tables.cuh"
+#include "sc_tracker.cuh"
+#include "sc_search.cuh"
+#include "sc_track_core.cuh"
+#include "sc_kernels.h"
+
+namespace sc {
+
+// ------------------------------------------------------------------------------------------------
+// fir(): 49-tap real-coefficient FIR on complex samples, in place, caller-owned delay line holding
+// the RAW past inputs, output scaled by GAIN.  One CTA per stream walks the samples in tiles of
+// 640 (128 threads x 5 consecutive outputs; lane stride 5 slots => conflict-free) with the last
+// 49 raw inputs carried in shared memory between tiles, so each sample is read and written once.
+// ext[0..48] = memory[0..48] (oldest first), ext[49 + j] = sample[j];
+// out[j] = GAIN * sum_k ext[j + 1 + k] * coeff[k], k ascending (src/fir.c:36-42).
+// ------------------------------------------------------------------------------------------------
+constexpr int FIR_THREADS = 128;
+constexpr int FIR_R = 5;
+constexpr int FIR_TILE = FIR_THREADS * FIR_R;          // 640
+
+template <bool WIDE>
+__global__ void __launch_bounds__(FIR_THREADS)
+fir_batch_kernel(float2 *__restrict__ memory, float2 *__restrict__ sample, long sample_stride, int length,
+                 long n_streams) {
+    __shared__ __align__(16) float2 ext[NTAPS + FIR_TILE + 8];
+    __shared__ float2 carry[NTAPS];
+    const int t = threadIdx.x;
+    for (long s = blockIdx.x; s < n_streams; s += gridDim.x) {
+        float2 *mem = memory + s * NTAPS;
+        float2 *x = sample + s * sample_stride;
+        if (t < NTAPS) ext[t] = mem[t];
+        __syncthreads();
+        for (int t0 = 0; t0 < length; t0 += FIR_TILE) {
+            const int n = min(FIR_TILE, length - t0);
+            for (int j = t; j < n; j += FIR_THREADS) ext[NTAPS + j] = x[t0 + j];
+            __syncthreads();
+            u64 acc[FIR_R];
+#pragma unroll
+            for (int r = 0; r < FIR_R; r++) acc[r] = 0ull;
+            if (FIR_R * t < n) {
+                const u64 *ep = reinterpret_cast<const u64 *>(ext) + FIR_R * t + 1;
+#pragma unroll
+                for (int j = 0; j < NTAPS + FIR_R - 1; j++) {
+                    const u64 v = ep[j];
+#pragma unroll
+                    for (int r = 0; r < FIR_R; r++) {
+                        const int k = j - r;
+                        if (k >= 0 && k < NTAPS) acc[r] = pk_add(acc[r], pk_mul_bcast_pz(v, tap<WIDE>(k)));
+                    }
+                }
+            }
+            if (t < NTAPS) carry[t] = ext[n + t];      // the last 49 raw inputs
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < FIR_R; r++) {
+                const int j = FIR_R * t + r;
+                if (j < n) {
+                    float yr, yi;
+                    unpk(acc[r], yr, yi);
+                    x[t0 + j] = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));
+                }
+            }
+            if (t < NTAPS) ext[t] = carry[t];
+            __syncthreads();
+        }
+        if (t < NTAPS) mem[t] = ext[t];
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_fir_batch(bool wide, long n_streams, float2 *memory, float2 *sample, long sample_stride,
+                             int length, cudaStream_t st) {
+    const int grid = (int) std::min<long>(n_streams, 148L * 16);
+    if (wide) fir_batch_kernel<true><<<grid, FIR_THREADS, 0, st>>>(memory, sample, sample_stride, length, n_streams);
+    else fir_batch_kernel<false><<<grid, FIR_THREADS, 0, st>>>(memory, sample, sample_stride, length, n_streams);
+    g_launch_count++;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// correlate() over lags 0..127 + the reference's argmax, one warp per stream.
+// ------------------------------------------------------------------------------------------------
+constexpr int SB_WARPS = 8;
+
+__global__ void __launch_bounds__(SB_WARPS * 32)
+search_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride, int *__restrict__ max_index,
+                    float *__restrict__ max_value, long n_streams) {
+    __shared__ __align__(16) float2 de[SB_WARPS][SEARCH_DE_SLOTS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long s = (long) blockIdx.x * SB_WARPS + warp; s < n_streams; s += (long) gridDim.x * SB_WARPS) {
+        const float2 *x = symbols + s * symbol_stride;
+        __syncwarp();
+        for (int i = lane; i < SEARCH_SYMS; i += 32) de[warp][de_pos(i)] = de_from_symbol(x[i]);
+        __syncwarp();
+        int bi;
+        float bv;
+        search_warp(de[warp], lane, bi, bv);
+        if (lane == 0) {
+            max_index[s] = bi;
+            max_value[s] = bv;
+        }
+    }
+}
+
+cudaError_t launch_search_batch(long n_streams, const float2 *symbols, long symbol_stride, int *max_index,
+                                float *max_value, cudaStream_t st) {
+    const int grid = (int) std::min<long>((n_streams + SB_WARPS - 1) / SB_WARPS, 148L * 8);
+    search_batch_kernel<<<grid, SB_WARPS * 32, 0, st>>>(symbols, symbol_stride, max_index, max_value, n_streams);
+    g_launch_count++;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// The decision half of qpsk_rx_frame() on explicit symbol windows dec[0..289], one thread per stream.
+// ------------------------------------------------------------------------------------------------
+struct RawLoader {
+    const float2 *dec;
+    int mi, ti;
+    __device__ __forceinline__ c32 x(int r) const { return from2(dec[min(mi + r, WIN - 1)]); }
+    __device__ __forceinline__ c32 y(int r) const { return from2(dec[min(max(ti + r, 0), WIN - 1)]); }
+};
+
+__global__ void __launch_bounds__(128)
+track_window_kernel(const float2 *__restrict__ symbols, long symbol_stride, const int *__restrict__ max_index,
+                    const float *__restrict__ max_value, int *__restrict__ rx_timing, uint32_t call_index,
+                    unsigned long long keystream, sc_frame_result *__restrict__ results, float *__restrict__ eq_dbg,
+                    long n_streams) {
+    const long s = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    RawLoader ld;
+    ld.dec = symbols + s * symbol_stride;
+    ld.mi = min(max(max_index[s], 0), PRE - 1);
+    ld.ti = rx_timing[s];
+    TrackOut o;
+    track_core(ld, o);
+    const int t_out = o.valid ? ld.mi + PRE : ld.ti;
+    rx_timing[s] = t_out;
+    store_result(results + s, o, keystream, max_value ? max_value[s] : 0.0f, ld.mi, t_out, call_index);
+    if (eq_dbg != nullptr) {
+#pragma unroll
+        for (int i = 0; i < EQ; i++) {
+            eq_dbg[s * 10 + 2 * i] = o.tk.C[i].r;
+            eq_dbg[s * 10 + 2 * i + 1] = o.tk.C[i].i;
+        }
+    }
+}
+
+cudaError_t launch_track_window_batch(long n_streams, const float2 *symbols, long symbol_stride,
+                                      const int *max_index, const float *max_value, int *rx_timing,
+                                      uint32_t call_index, unsigned long long keystream,
+                                      sc_frame_result *results, float *eq_dbg, cudaStream_t st) {
+    const int grid = (int) ((n_streams + 127) / 128);
+    track_window_kernel<<<grid, 128, 0, st>>>(symbols, symbol_stride, max_index, max_value, rx_timing, call_index,
+                                              keystream, results, eq_dbg, n_streams);
+    g_launch_count++;
+    return cudaGetLastError();
+}
+
+}  // namespace sc

@@ -1,0 +1,110 @@
+"""Drop-in boundary on the GPU: a C program written against the reference's headers, compiled against
+include/sc_compat and linked with libsinglecarrier_b200.so, must print what the reference prints."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def dropin_output(tmp_path_factory):
+    exe = tmp_path_factory.mktemp("dropin") / "dropin_main"
+    libdir = os.path.join(ROOT, "singlecarrier_b200")
+    subprocess.run(["gcc", "-std=gnu11", "-O2", "-I", os.path.join(ROOT, "include", "sc_compat"),
+                    os.path.join(ROOT, "tests", "dropin_main.c"), "-o", str(exe), "-L", libdir,
+                    "-lsinglecarrier_b200", "-lm", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe), os.path.join(ROOT, "tests", "golden", "preamble_qpsk_8k.raw")],
+                         check=True, capture_output=True, text=True, timeout=300).stdout
+    return out.strip().splitlines()
+
+
+def test_dropin_program_matches_reference(dropin_output, gold, oracle):
+    lines = dropin_output
+    txp = lines[0].split()
+    assert txp[0] == "TXP" and txp[1] == "640"
+    assert [int(v) for v in txp[2:]] == [0, -45, -72, -20, -6, -74, -112, -13, -22, -158, -111, -3, -251, -462, -160,
+                                         7, -628, -972, -99, 397, -885, -1602, 1044, 4959]
+    # data frame right after the preamble: oracle TX with the same bits
+    st = oracle.new_state()
+    oracle.tx_preamble(st)
+    obits = np.array([(i * 7 + 3) % 5 < 2 for i in range(62)], np.uint8)
+    frame = oracle.tx_data(st, obits)
+    acc = 0
+    for v in frame.tolist():
+        acc = (acc * 31 + v)
+        acc = (acc + 2 ** 63) % 2 ** 64 - 2 ** 63                            # C long wrap-around
+    assert lines[1].split() == ["TXD", "155", str(acc)]
+    g = gold("rx_shipped.npz")
+    rx = [ln.split() for ln in lines if ln.startswith("RX ")]
+    assert len(rx) == 14
+    for n, f in enumerate(rx):
+        assert int(f[2]) == g["valid"][n]
+        if g["valid"][n]:
+            assert f[3] == "".join(map(str, g["bits"][n]))
+        assert np.float32(float(f[-2])) == g["eq_coeff"][n][0] and np.float32(float(f[-1])) == g["eq_coeff"][n][9]
+    ks = [ln for ln in lines if ln.startswith("KS ")][0].split()
+    assert ks[1] == "".join(map(str, gold("stage_golden.npz")["keystream"][:62])) and ks[2] == "-1"
+    assert ks[1].startswith("000000111111011000001000001101")                # DVB PRBS, SURVEY section 4 pin 3
+    misc = [ln for ln in lines if ln.startswith("MISC ")][0].split()
+    assert float(misc[1]) == 25.0 and misc[2] == "01"                        # bits[0] = Q (im<0), bits[1] = I (re<0)
+    fir_line = [ln for ln in lines if ln.startswith("FIR ")][0].split()
+    m = np.zeros(49, np.complex64)
+    x = np.array([1, 0, 0, 0, 0, 1j, 0, 0], np.complex64)
+    oracle.fir(m, False, x)
+    assert [np.float32(float(v)) for v in fir_line[1:]] == [x[0].real, x[4].real, x[7].imag]
+
+
+def test_legacy_l1_symbols_via_ctypes(gold):
+    """train_eq / data_eq / kalman_* / exported globals against the reference trajectory."""
+    import singlecarrier_b200 as sc
+    L = sc.lib
+    g = gold("stage_golden.npz")
+    L.train_eq.restype = C.c_float
+    L.train_eq.argtypes = [C.c_void_p, C.c_int, C.c_float]
+    L.data_eq.restype = C.c_float
+    L.data_eq.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.scramble_init.argtypes = [C.c_int]
+    eq = np.frombuffer((C.c_float * 10).in_dll(L, "eq_coeff"), np.float32)
+    gain = np.frombuffer((C.c_float * 10).in_dll(L, "kalman_gain"), np.float32)
+    ky = C.c_float.in_dll(L, "kalman_y")
+    sym = g["eq_sym"].copy()
+    L.kalman_init()
+    L.scramble_init(2)
+    L.scramble_init(1)
+    rets = []
+    for i in range(128):
+        rets.append(L.train_eq(sym.ctypes.data, i, float(g["eq_ref"][i])))
+        assert np.array_equal(eq.view(np.uint32), g["eq_traj"][i].view(np.float32).view(np.uint32)), i
+    dibits = []
+    for i in range(31):
+        d = C.c_uint8(0)
+        rets.append(L.data_eq(C.byref(d), sym.ctypes.data, 128 + i))
+        dibits.append(d.value)
+        assert np.array_equal(eq.view(np.uint32), g["eq_traj"][128 + i].view(np.float32).view(np.uint32)), i
+    assert np.array_equal(np.array(rets, np.float32).view(np.uint32), g["eq_ret"].view(np.uint32))
+    assert dibits == g["eq_dibits"].tolist()
+    assert np.array_equal(gain.view(np.uint32), g["eq_gain"].view(np.float32).view(np.uint32))
+    assert np.float32(ky.value).view(np.uint32) == g["eq_y"].view(np.uint32)
+    # fft.h through the legacy symbols
+    f = gold("fft_golden.npz")
+    L.fft_alloc.restype = C.c_void_p
+    L.fft_alloc.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.fft.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    for n in (64, 60):
+        cfg = L.fft_alloc(n, 0, None, None)
+        out = np.zeros(n, np.complex64)
+        L.fft(cfg, f[f"c{n}_in"].ctypes.data, out.ctypes.data)
+        assert np.array_equal(out.view(np.uint32), f[f"c{n}_0"].view(np.uint32))
+    L.fftr_alloc.restype = C.c_void_p
+    L.fftr_alloc.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    assert L.fftr_alloc(63, 0, None, None) is None                           # odd length -> NULL (src/fft.c:89-91)
+    cf = L.fftr_alloc(64, 0, None, None)
+    spec = np.zeros(33, np.complex64)
+    L.fftr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fftr(cf, f["r64_in"].ctypes.data, spec.ctypes.data)
+    assert np.array_equal(spec.view(np.uint32), f["r64_spec"].view(np.uint32))
