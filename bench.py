@@ -148,8 +148,7 @@ def run_reference_arm(args, rank, world):
         print(f"[bench] reference arm: device synthesis unavailable ({e}); using oracle TX", file=sys.stderr)
     if sample is None:
         from oracle import pyoracle as po
-        from tests.helpers import synth_streams
-        sample = synth_streams(po.Oracle(), np.random.default_rng(args.seed), streams, n_frames)
+        sample = po.synth_streams(po.Oracle(), np.random.default_rng(args.seed), streams, n_frames)
     np.save(path, sample)
     r = cpu_bench.run(path, n_frames, None, args.warmup + args.steps)
     os.unlink(path)

@@ -152,6 +152,32 @@ class Oracle:
         return out[0]
 
 
+def synth_streams(oracle, rng, n_streams, n_frames, noise_levels=(0.0, 30.0, 300.0, 1500.0, 4000.0),
+                  max_lead=2000, gaps=(903, 0, 500, 1880)):
+    """Oracle-TX loop-back streams with random lead-in, dead air and additive noise -> int16[n, n_frames*1880]."""
+    total = n_frames * FRAME_SIZE
+    out = np.zeros((n_streams, total), np.int16)
+    for s in range(n_streams):
+        st = oracle.new_state()
+        lead = int(rng.integers(0, max_lead))
+        gap = int(gaps[s % len(gaps)])
+        parts = [np.zeros(lead, np.int16)]
+        n = lead
+        while n < total:
+            parts.append(oracle.tx_preamble(st))
+            for _ in range(8):
+                parts.append(oracle.tx_data(st, rng.integers(0, 2, 62).astype(np.uint8)))
+            parts.append(np.zeros(gap, np.int16))
+            n += 1880 + gap
+        x = np.concatenate(parts)[:total].astype(np.float64)
+        noise = noise_levels[s % len(noise_levels)]
+        if noise > 0:
+            x = x + rng.normal(0, noise, total)
+        out[s] = np.clip(x, -32767, 32767).round().astype(np.int16)
+    return out
+
+
+
 class RefStats(C.Structure):
     """ref_frame_stats (oracle/ref_harness_post.c)."""
     _fields_ = [("valid", C.c_int32), ("max_index", C.c_int32), ("matches", C.c_int32),

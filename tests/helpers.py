@@ -4,29 +4,7 @@ import numpy as np
 from oracle import pyoracle as po
 
 
-def synth_streams(oracle, rng, n_streams, n_frames, noise_levels=(0.0, 30.0, 300.0, 1500.0, 4000.0),
-                  max_lead=2000, gaps=(903, 0, 500, 1880)):
-    """Oracle-TX loop-back streams with random lead-in, dead air and additive noise -> int16[n, n_frames*1880]."""
-    total = n_frames * po.FRAME_SIZE
-    out = np.zeros((n_streams, total), np.int16)
-    for s in range(n_streams):
-        st = oracle.new_state()
-        lead = int(rng.integers(0, max_lead))
-        gap = int(gaps[s % len(gaps)])
-        parts = [np.zeros(lead, np.int16)]
-        n = lead
-        while n < total:
-            parts.append(oracle.tx_preamble(st))
-            for _ in range(8):
-                parts.append(oracle.tx_data(st, rng.integers(0, 2, 62).astype(np.uint8)))
-            parts.append(np.zeros(gap, np.int16))
-            n += 1880 + gap
-        x = np.concatenate(parts)[:total].astype(np.float64)
-        noise = noise_levels[s % len(noise_levels)]
-        if noise > 0:
-            x = x + rng.normal(0, noise, total)
-        out[s] = np.clip(x, -32767, 32767).round().astype(np.int16)
-    return out
+synth_streams = po.synth_streams
 
 
 def oracle_results(oracle, samples, n_frames, wide=False, foffset=0.0):
