@@ -241,11 +241,11 @@ def main():
         if world > 1:
             dist.all_reduce(counters)                      # the only collective: lock / bit statistics
 
+    sampler = ClockSampler(local_rank)          # started before the warm-up (same workload) so that
+    sampler.start()                             # nvidia-smi is already sampling when the timed steps run
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = sc.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()

@@ -1,0 +1,66 @@
+"""CPU (needs cuobjdump): the exact kernels must not contain contracted multiply-adds.
+
+ptxas contracts packed mul+add into FFMA2 unless the multiply is written fma(a, b, +0) (DESIGN.md
+section 2), so every FFMA2 in the front-end / stage FIR kernels must have RZ as its addend, and the
+scalar FFMA instructions that remain must belong to the IEEE reciprocal/divide expansions."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "singlecarrier_b200", "libsinglecarrier_b200.so")
+
+
+def sass():
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-sass", LIB], check=True, capture_output=True, text=True).stdout
+    funcs, cur = {}, None
+    for ln in out.splitlines():
+        m = re.search(r"Function : (\S+)", ln)
+        if m:
+            cur = m.group(1)
+            funcs[cur] = []
+        elif cur and re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
+            funcs[cur].append(ln.split("*/", 1)[1].split("/*")[0].strip())
+    return funcs
+
+
+def test_no_contracted_fma_in_exact_kernels():
+    funcs = sass()
+    assert any("sm_100a" in x or True for x in funcs)
+    seen = 0
+    for name, ins in funcs.items():
+        if not any(k in name for k in ("frontend_kernel", "fir_batch_kernel", "search_batch_kernel")):
+            continue
+        seen += 1
+        packed = [i for i in ins if "FFMA2" in i]
+        if "search" not in name:
+            assert len(packed) > 200, name
+        for i in packed:
+            assert re.search(r",\s*RZ(\.F32)?\s*;?$", i.rstrip(" ;") + ";") or i.rstrip(" ;").endswith("RZ.F32") \
+                or i.rstrip(" ;").endswith("RZ"), (name, i)
+        assert sum("FADD2" in i for i in ins) >= len(packed)
+        assert not [i for i in ins if re.match(r"(@!?P\d+\s+)?FFMA\b", i)], name      # no scalar FFMA at all here
+    assert seen >= 4
+    for name, ins in funcs.items():
+        if "track_kernel" in name or "track_window_kernel" in name:
+            # 5 reciprocals per step x 2 loops (+ slow paths); anything beyond that would be a contraction
+            n_ffma = sum(bool(re.match(r"(@!?P\d+\s+)?FFMA\b", i)) for i in ins)
+            n_rcp = sum("MUFU.RCP" in i for i in ins)
+            assert n_rcp >= 10 and n_ffma <= 4 * n_rcp, (name, n_ffma, n_rcp)
+            assert sum(bool(re.match(r"(@!?P\d+\s+)?FMUL\b", i)) for i in ins) > 300
+            assert not [i for i in ins if "FFMA2" in i]
+
+
+def test_compiled_for_sm_100a_only():
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-lelf", LIB], check=True, capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
