@@ -199,6 +199,11 @@ int sc_fftri_batch_dev(int device, int64_t n_batches, int nfft, const float *in,
 int sc_lock_stats_dev(int device, const sc_frame_result *results, int64_t n_streams, int64_t result_stride,
                       int n_frames, uint64_t *counters, void *stream);
 
+/* Self-test: number of float bit patterns in [lo_bits, hi_bits] (as IEEE binary32) for which the
+ * tracking kernel's branch-free reciprocal differs from the correctly rounded one (expected 0 for
+ * 2^-120 .. 2^120).  *mismatches: device uint64, accumulated into. */
+int sc_selftest_rcp_dev(int device, uint32_t lo_bits, uint32_t hi_bits, uint64_t *mismatches, void *stream);
+
 /* ---- small utilities used by host code and tests --------------------------------------- */
 
 /* RX/TX NCO phasor table exactly as the reference's recurrences generate it (qpsk.c:138-147,

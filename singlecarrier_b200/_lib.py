@@ -65,6 +65,7 @@ def _load() -> C.CDLL:
     sig("sc_fftr_batch_dev", i32, i32, i64, i32, vp, vp, vp)
     sig("sc_fftri_batch_dev", i32, i32, i64, i32, vp, vp, vp)
     sig("sc_lock_stats_dev", i32, i32, vp, i64, i64, i32, vp, vp)
+    sig("sc_selftest_rcp_dev", i32, i32, u32, u32, vp, vp)
     sig("sc_nco_table_host", i32, vp, i32, u32, i32, vp)
     sig("sc_keystream_word", u64, u32)
     return lib

@@ -743,3 +743,13 @@ extern "C" int sc_profile_read(sc_modem *m, double out[4]) {
     if (rc != SC_OK) return rc;
     return prof_sum(m->ev_tk, &out[2], &out[3]);
 }
+
+// Self-test hook (tests/test_stage_gpu.py): counts float bit patterns in [lo_bits, hi_bits] for which
+// the tracker's branch-free reciprocal differs from __frcp_rn.  *mismatches is a device uint64.
+extern "C" int sc_selftest_rcp_dev(int device, uint32_t lo_bits, uint32_t hi_bits, uint64_t *mismatches, void *stream) {
+    if (!mismatches || hi_bits < lo_bits) return fail(SC_EINVAL, "sc_selftest_rcp_dev: bad arguments");
+    int rc = stage_device(device);
+    if (rc != SC_OK) return rc;
+    CU(launch_selftest_rcp(lo_bits, hi_bits, (unsigned long long *) mismatches, (cudaStream_t) stream));
+    return SC_OK;
+}

@@ -41,6 +41,8 @@ constexpr int FFT_SCRATCH_CTAS = 64;
 cudaError_t launch_fft(const FftPlan &plan, const float2 *tw, const float2 *super_tw, int mode, const void *in,
                        void *out, float2 *scratch, long n_batches, cudaStream_t st);
 
+cudaError_t launch_selftest_rcp(unsigned lo, unsigned hi, unsigned long long *mismatches, cudaStream_t st);
+
 // sc_stats_kernels.cu
 cudaError_t launch_lock_stats(const sc_frame_result *results, long n_streams, long result_stride, int n_frames,
                               unsigned long long *counters, cudaStream_t st);

@@ -162,4 +162,23 @@ cudaError_t launch_track_window_batch(long n_streams, const float2 *symbols, lon
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Self-test: rcp_rn_normal() (sc_exact.cuh) against __frcp_rn over a range of float bit patterns.
+// ------------------------------------------------------------------------------------------------
+__global__ void selftest_rcp_kernel(unsigned lo, unsigned hi, unsigned long long *mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long b = (unsigned long long) lo + (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+         b <= hi; b += (unsigned long long) gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned) b);
+        if (__float_as_uint(rcp_rn_normal(x)) != __float_as_uint(__frcp_rn(x))) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+cudaError_t launch_selftest_rcp(unsigned lo, unsigned hi, unsigned long long *mismatches, cudaStream_t st) {
+    selftest_rcp_kernel<<<148 * 16, 256, 0, st>>>(lo, hi, mismatches);
+    g_launch_count++;
+    return cudaGetLastError();
+}
+
 }  // namespace sc

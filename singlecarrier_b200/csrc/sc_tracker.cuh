@@ -56,14 +56,29 @@ struct Tracker {
 
         const float hq = __fadd_rn(1.0f, q);                          // 6.7
         const float ht = __fmul_rn(A[EQ - 1], q);
-        KY = __frcp_rn(__fadd_rn(A[0], ht));                          // 6.19
+
+        // kalman_y takes the values 1/(a[j] + ht), j = 0..4 (6.19, 6.22).  All five denominators
+        // are known here, so the reciprocals are taken together (off the serial chain) behind one
+        // range test instead of five: a[] is non-decreasing (d[] > 0), so den[0] and den[4] bound them.
+        float den[EQ], rc[EQ];
+#pragma unroll
+        for (int j = 0; j < EQ; j++) den[j] = __fadd_rn(A[j], ht);
+        if (den[0] >= 0x1p-120f && den[EQ - 1] <= 0x1p120f) {
+#pragma unroll
+            for (int j = 0; j < EQ; j++) rc[j] = rcp_rn_normal(den[j]);
+        } else {                                                      // never seen in practice; NaNs land here
+#pragma unroll
+            for (int j = 0; j < EQ; j++) rc[j] = __frcp_rn(den[j]);
+        }
+
+        KY = rc[0];                                                   // 6.19
         D[0] = __fmul_rn(D[0], __fmul_rn(__fmul_rn(hq, __fadd_rn(E, ht)), KY));   // 6.20
 
 #pragma unroll
         for (int j = 1; j < EQ; j++) {                                // 6.10 - 6.16
-            const float B = __fadd_rn(A[j - 1], ht);                  // 6.21
+            const float B = den[j - 1];                               // 6.21: a[j-1] + ht
             const c32 H = mk(__fmul_rn(-F[j].r, KY), __fmul_rn(-F[j].i, KY));      // 6.11
-            KY = __frcp_rn(__fadd_rn(A[j], ht));                      // 6.22
+            KY = rc[j];                                               // 6.22
             D[j] = __fmul_rn(D[j], __fmul_rn(__fmul_rn(hq, B), KY));  // 6.13
 #pragma unroll
             for (int i = 0; i < j; i++) {

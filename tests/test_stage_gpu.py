@@ -217,3 +217,15 @@ def test_lock_stats_counters(sc, oracle):
     assert c[5] == sum(bin(int(b)).count("1") for b in r["bits"][v])
     assert c[8:].sum() == ns * nf
     bank.close()
+
+
+def test_branch_free_reciprocal_is_correctly_rounded(sc):
+    """Every float in [2^-120, 2^120] (2.0e9 bit patterns): rcp_rn_normal == __frcp_rn, bit for bit."""
+    import struct
+    import torch
+    lo = struct.unpack("<I", struct.pack("<f", 2.0 ** -120))[0]
+    hi = struct.unpack("<I", struct.pack("<f", 2.0 ** 120))[0]
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    sc._lib.check(sc.lib.sc_selftest_rcp_dev(0, lo, hi, bad.data_ptr(), 0))
+    torch.cuda.synchronize()
+    assert hi - lo > 2_000_000_000 and int(bad.item()) == 0
