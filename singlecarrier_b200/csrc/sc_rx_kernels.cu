@@ -64,14 +64,15 @@ constexpr int FE_R = 5;                                     // outputs per lane 
 constexpr int FE_FIR_LANES = 29;
 constexpr int FE_PASS_OUT = FE_FIR_LANES * FE_R;            // 145
 constexpr int FE_PASS_SAMP = NTAPS + CYC * (FE_PASS_OUT - 1);   // 769
-constexpr int FE_FRONT = 2;                                 // slack slots in front (pair alignment)
-constexpr int FE_BUF = 784;                                 // FE_FRONT + 769 + pair slack, rounded
+constexpr int FE_FRONT = 2;                                 // slack slots in front (pair alignment), +1 for parity
+constexpr int FE_BUF = 784;                                 // FE_FRONT + 1 + 769 + pair slack, rounded
 constexpr int FE_NPAIR = (FE_NSAMP + 2 + 1) / 2;            // 748 int16 pairs cover any alignment
 constexpr int FE_PAIRS_PER_LANE = (FE_NPAIR + 31) / 32;     // 24
-constexpr int FE_DE_SLOTS = SEARCH_DE_SLOTS;                 // pos(x) = x + x/4, x < 255
+constexpr int FE_DE_SLOTS = (SEARCH_WORDS + 1) / 2;           // the search operands (floats) in float2 slots
 static_assert(WIN == 2 * FE_PASS_OUT, "290 = 2 x 145");
 static_assert(WIN + FE_DE_SLOTS <= FE_BUF, "W and (d,e) reuse the mixed-sample region");
-static_assert(FE_FRONT + FE_PASS_SAMP + 2 <= FE_BUF, "pass buffer");
+static_assert(FE_FRONT + 1 + FE_PASS_SAMP + 2 <= FE_BUF, "pass buffer");
+static_assert((WIN * 2) % 32 == 4, "search arrays start 4 banks after W: fine, only their relative offset matters");
 
 // Stage the mixed samples rel in [h0, h0 + 769) of the stream-frame into buf (slot FE_FRONT + rel - h0).
 // Pair p holds samples rel = 2p - shift and 2p + 1 - shift; out-of-range slots land in the slack.
@@ -92,19 +93,21 @@ __device__ __forceinline__ void fe_load(uint32_t (&raw)[FE_KN], const uint32_t *
 
 template <int K_LO>
 __device__ __forceinline__ void fe_stage(float2 *__restrict__ buf, const uint32_t (&rawk)[FE_KN],
-                                         const float2 *__restrict__ tab, int lane, int shift, int h0) {
+                                         const float2 *__restrict__ tab, int lane, int off) {
+    // off = front - shift - h0 is even (front is chosen per pass to make it so), hence every pair
+    // lands on a 16-byte boundary and is written with one conflict-free 128-bit store
 #pragma unroll
     for (int kk = 0; kk < FE_KN; kk++) {
         const int k = kk + K_LO;
         const uint32_t (&raw)[FE_KN] = rawk;
         const int p = lane + 32 * k;
-        const int d = FE_FRONT + 2 * p - shift - h0;          // slot of the pair's first sample
+        const int d = 2 * p + off;                            // slot of the pair's first sample
         if (d >= 0 && d + 1 < FE_BUF && p < FE_NPAIR) {
             const float4 ph = __ldg(reinterpret_cast<const float4 *>(tab + 2 * p));
             const float v0 = (float) (int16_t) (raw[kk] & 0xffffu);
             const float v1 = (float) (int16_t) (raw[kk] >> 16);
-            buf[d] = make_float2(__fmul_rn(ph.x, v0), __fmul_rn(ph.y, v0));       // qpsk.c:141
-            buf[d + 1] = make_float2(__fmul_rn(ph.z, v1), __fmul_rn(ph.w, v1));
+            *reinterpret_cast<float4 *>(buf + d) = make_float4(__fmul_rn(ph.x, v0), __fmul_rn(ph.y, v0),     // qpsk.c:141
+                                                               __fmul_rn(ph.z, v1), __fmul_rn(ph.w, v1));
         }
     }
 }
@@ -112,10 +115,10 @@ __device__ __forceinline__ void fe_stage(float2 *__restrict__ buf, const uint32_
 // 49-tap RRC at 5 consecutive decimated instants per lane (src/fir.c:36-42): y += mem[i]*coeff[i]
 // left to right, both components at once (packed f32x2, see sc_exact.cuh).
 template <bool WIDE>
-__device__ __forceinline__ void fe_fir(const float2 *__restrict__ buf, int lane, u64 (&acc)[FE_R]) {
+__device__ __forceinline__ void fe_fir(const float2 *__restrict__ buf, int front, int lane, u64 (&acc)[FE_R]) {
 #pragma unroll
     for (int r = 0; r < FE_R; r++) acc[r] = 0ull;
-    const u64 *mp = reinterpret_cast<const u64 *>(buf) + FE_FRONT + CYC * FE_R * lane;
+    const u64 *mp = reinterpret_cast<const u64 *>(buf) + front + CYC * FE_R * lane;
 #pragma unroll
     for (int j = 0; j < NTAPS + CYC * (FE_R - 1); j++) {
         const u64 x = mp[j];
@@ -174,13 +177,14 @@ frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2
 #pragma unroll 1
     for (int h = 0; h < 2; h++) {
         const int h0 = h * CYC * FE_PASS_OUT;
+        const int front = FE_FRONT + ((shift + h0) & 1);       // makes every staged pair 16-byte aligned
         if (active) {
             if (fast) {
                 if (h == 0) {
-                    fe_stage<FE_KA_LO>(mix, raw, tab, lane, shift, 0);
+                    fe_stage<FE_KA_LO>(mix, raw, tab, lane, front - shift - h0);
                     fe_load<FE_KB_LO>(raw, fp, lane, base2);       // pass B's loads fly during pass A's FIR
                 } else {
-                    fe_stage<FE_KB_LO>(mix, raw, tab, lane, shift, CYC * FE_PASS_OUT);
+                    fe_stage<FE_KB_LO>(mix, raw, tab, lane, front - shift - h0);
                 }
             } else {
                 // generic path (odd byte alignment, or the cold-start timing T < 48 where samples
@@ -193,7 +197,7 @@ frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2
                         const float2 ph = __ldg(mix_table + t);
                         v = make_float2(__fmul_rn(ph.x, x), __fmul_rn(ph.y, x));
                     }
-                    mix[FE_FRONT + rel] = v;
+                    mix[front + rel] = v;
                 }
             }
         }
@@ -201,7 +205,7 @@ frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2
         u64 acc[FE_R];
 #pragma unroll
         for (int r = 0; r < FE_R; r++) acc[r] = 0ull;
-        if (active && lane < FE_FIR_LANES) fe_fir<WIDE>(mix, lane, acc);
+        if (active && lane < FE_FIR_LANES) fe_fir<WIDE>(mix, front, lane, acc);
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < FE_R; r++) {
@@ -210,23 +214,23 @@ frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2
         }
     }
 
-    float2 *W = mix;                       // [290]
-    float2 *DE = mix + WIN;                // [320], pos(x) = x + x/4
+    float2 *W = mix;                                        // [290]
+    float *DE = reinterpret_cast<float *>(mix + WIN);       // search operands, sc_search.cuh
     if (active && lane < FE_FIR_LANES) {
 #pragma unroll
         for (int r = 0; r < FE_R; r++) {
             float yr, yi;
             unpk(accA[r], yr, yi);
-            W[FE_R * lane + r] = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));    // src/fir.c:42
+            const float2 wa = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));       // src/fir.c:42
             unpk(accB[r], yr, yi);
-            W[FE_PASS_OUT + FE_R * lane + r] = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));
+            const float2 wb = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));
+            const int xa = FE_R * lane + r, xb = FE_PASS_OUT + xa;
+            W[xa] = wa;
+            W[xb] = wb;
+            // ---- stage 3 operands straight from the registers (qpsk.c:88-96, see sc_search.cuh)
+            de_store(DE, xa, wa);
+            if (xb < SEARCH_SYMS) de_store(DE, xb, wb);
         }
-    }
-    __syncwarp();
-
-    // ---- stage 3: preamble search (qpsk.c:88-96, 172-183), see sc_search.cuh ----
-    if (active) {
-        for (int x = lane; x < SEARCH_SYMS; x += 32) DE[de_pos(x)] = de_from_symbol(W[x]);
     }
     __syncwarp();
 

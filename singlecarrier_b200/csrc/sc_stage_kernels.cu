@@ -91,12 +91,12 @@ constexpr int SB_WARPS = 8;
 __global__ void __launch_bounds__(SB_WARPS * 32)
 search_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride, int *__restrict__ max_index,
                     float *__restrict__ max_value, long n_streams) {
-    __shared__ __align__(16) float2 de[SB_WARPS][SEARCH_DE_SLOTS];
+    __shared__ __align__(16) float de[SB_WARPS][SEARCH_WORDS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (long s = (long) blockIdx.x * SB_WARPS + warp; s < n_streams; s += (long) gridDim.x * SB_WARPS) {
         const float2 *x = symbols + s * symbol_stride;
         __syncwarp();
-        for (int i = lane; i < SEARCH_SYMS; i += 32) de[warp][de_pos(i)] = de_from_symbol(x[i]);
+        for (int i = lane; i < SEARCH_SYMS; i += 32) de_store(de[warp], i, x[i]);
         __syncwarp();
         int bi;
         float bv;
