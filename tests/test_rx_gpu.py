@@ -137,3 +137,43 @@ def test_device_api_and_strides(sc, oracle):
     obits, ostats = oracle_results(oracle, samples, nf)
     assert compare_results(res, None, obits, ostats) == []
     assert (res["call_index"] == np.arange(nf)[None, :]).all()
+
+
+def test_odd_strides_use_the_generic_load_path(sc, oracle):
+    """Streams whose first sample is not 4-byte aligned (odd stream stride) take the scalar-load path of
+    the front-end; results must not change."""
+    import torch
+    rng = np.random.default_rng(13)
+    nf, ns = 6, 21
+    samples = synth_streams(oracle, rng, ns, nf)
+    stride = nf * 1880 + 3                                              # odd: every other stream starts at an odd sample
+    flat = torch.zeros(ns * stride + 8, dtype=torch.int16, device="cuda")
+    d_in = flat[1:1 + ns * stride].view(ns, stride)                     # and the base pointer itself is 2-byte aligned only
+    d_in[:, : nf * 1880] = torch.from_numpy(samples).cuda()
+    assert d_in.data_ptr() % 4 == 2 and d_in.stride(0) % 2 == 1
+    d_res = torch.zeros((ns, nf * 32), dtype=torch.uint8, device="cuda")
+    bank = sc.ModemBank(ns)
+    bank.rx_frames_dev(d_in, nf, d_res)
+    torch.cuda.synchronize()
+    res = d_res.cpu().numpy().view(sc.RESULT_DTYPE)
+    bank.close()
+    obits, ostats = oracle_results(oracle, samples, nf)
+    assert compare_results(res, None, obits, ostats) == []
+
+
+def test_argument_validation(sc):
+    import ctypes as C
+    L = sc.lib
+    h = C.c_void_p()
+    assert L.sc_create(C.byref(h), 0, 0, 0, 0.0) == -1                   # n_streams must be positive
+    assert L.sc_create(C.byref(h), 99, 4, 0, 0.0) == -1                  # no such device
+    assert b"device" in L.sc_last_error()
+    bank = sc.ModemBank(4)
+    x = np.zeros((4, 1880), np.int16)
+    r = np.zeros((4, 1), sc.RESULT_DTYPE)
+    assert L.sc_rx_frames_host(bank._h, x.ctypes.data, 100, 1, r.ctypes.data, 1, None) == -1      # stride < batch
+    assert L.sc_rx_frames_host(bank._h, x.ctypes.data, 1880, 1, r.ctypes.data, 1, r.ctypes.data) == -1  # eq_dbg w/o flag
+    assert L.sc_rx_frames_host(bank._h, x.ctypes.data, 1880, 0, r.ctypes.data, 1, None) == 0      # empty batch is a no-op
+    assert bank.call_index == 0
+    assert L.sc_fft_batch_dev(0, 1, 0, 0, x.ctypes.data, x.ctypes.data, None) == -1
+    bank.close()
