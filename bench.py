@@ -46,6 +46,10 @@ TK_BYTES = 198 * 8 + 12 + 32 + 4           # tracker window + (idx,val,timing) +
 CHAIN_BYTES = 1880 * 2 + 32                # int16 frame in + result record out
 FE_OPS = 2 * 1494 + 290 * 198 + 2 * 255 + 128 * 128 * 2 + 128 * 3
 TK_OPS = 128 * 398 + 31 * 397
+# DRAM traffic per stream-frame from the ncu --set full capture (dram__bytes_read.sum + dram__bytes_write.sum
+# divided by the 131,072 stream-frames of one launch): profiles/r01_ncu_summary.md
+FE_DRAM_TRAFFIC = (403.762944e6 + 179.029504e6) / 131072
+TK_DRAM_TRAFFIC = (186.173440e6 + 7.513088e6) / 131072
 
 
 def peaks():
@@ -280,15 +284,18 @@ def main():
     clk = (clocks.get("sm_mhz") or sm_max) * 1e6
     fp32_peak = 148 * 128 * clk
 
-    def roof(name, ms_launch, bytes_sf, ops_sf):
+    def roof(name, ms_launch, bytes_sf, ops_sf, traffic_sf):
         gbs = streams * bytes_sf / (ms_launch * 1e-3) / 1e9
         ops = streams * ops_sf / (ms_launch * 1e-3)
         return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                "traffic": None, "ms_per_launch": ms_launch, "bytes_per_stream_frame": bytes_sf,
+                "traffic": streams * traffic_sf, "traffic_source": "ncu --set full, profiles/r01_ncu_summary.md, scaled to this launch's streams",
+                "algorithmic_bytes_per_launch": streams * bytes_sf,
+                "ms_per_launch": ms_launch, "bytes_per_stream_frame": bytes_sf,
                 "fp32_issue": {"achieved_tops": ops / 1e12, "peak_tops": fp32_peak / 1e12, "frac": ops / fp32_peak,
                                "ops_per_stream_frame": ops_sf, "note": "exact-order FP32 (no FMA): the true bound, SURVEY F8"}}
 
-    fe, tk = roof("frontend_kernel", fe_ms, FE_BYTES, FE_OPS), roof("track_kernel", tk_ms, TK_BYTES, TK_OPS)
+    fe = roof("frontend_kernel", fe_ms, FE_BYTES, FE_OPS, FE_DRAM_TRAFFIC)
+    tk = roof("track_kernel", tk_ms, TK_BYTES, TK_OPS, TK_DRAM_TRAFFIC)
     dom, other = (tk, fe) if tk_ms >= fe_ms else (fe, tk)
     roofline = dict(dom)
     roofline["peak_source"] = peak_src

@@ -15,6 +15,8 @@
 #include "sc_track_core.cuh"
 #include "sc_kernels.h"
 
+#include <stdlib.h>
+
 namespace sc {
 
 
@@ -323,11 +325,12 @@ cudaError_t launch_frontend(bool wide, const int16_t *in, long stream_stride, co
                             const int *timing_cur, const int *timing_next, float2 *win, int *max_index,
                             float *max_value, int n_streams, cudaStream_t st) {
     const int grid = (n_streams + FE_WARPS - 1) / FE_WARPS;
+    static const int extra_smem = getenv("SC_FE_EXTRA_SMEM") ? atoi(getenv("SC_FE_EXTRA_SMEM")) : 0;   // occupancy experiments
     if (wide)
-        frontend_kernel<true><<<grid, FE_WARPS * 32, 0, st>>>(in, stream_stride, mix_table, timing_cur, timing_next,
+        frontend_kernel<true><<<grid, FE_WARPS * 32, extra_smem, st>>>(in, stream_stride, mix_table, timing_cur, timing_next,
                                                               win, max_index, max_value, n_streams);
     else
-        frontend_kernel<false><<<grid, FE_WARPS * 32, 0, st>>>(in, stream_stride, mix_table, timing_cur, timing_next,
+        frontend_kernel<false><<<grid, FE_WARPS * 32, extra_smem, st>>>(in, stream_stride, mix_table, timing_cur, timing_next,
                                                                win, max_index, max_value, n_streams);
     g_launch_count++;
     return cudaGetLastError();

@@ -1,0 +1,6 @@
+for x in 0 8000 14000; do for p in 2 3 4 6; do
+SC_FE_EXTRA_SMEM=$x python bench.py --no-e2e --no-cpu --slab-parts $p --steps 4 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); r=d['roofline']; o=r['other_kernel']
+print('extra_smem',$x,'parts',$p,'value %.0f Msym/s  ms/step %.2f | %s %.3f | %s %.3f'%(d['value'],d['ms_per_step'],r['kernel'],r['ms_per_launch'],o['kernel'],o['ms_per_launch']))"
+done; done
