@@ -160,7 +160,11 @@ int sc_tx_channel_dev(sc_modem *m, const uint8_t *bits, uint8_t *bits_out, uint6
 /* ---- stage entry points (device pointers; batched forms of the reference's L1 functions) -- */
 
 /* fir(), fir.h:19 / src/fir.c:22-44, for n_streams independent (memory, sample) pairs:
- * memory[s*49 .. +49), sample[s*sample_stride .. +length) complex float, both updated in place. */
+ * memory[s*49 .. +49), sample[s*sample_stride .. +length) complex float, both updated in place.
+ * wide: bit 0 = the reference's `choice` (alpha=0.5 taps); bit 1 = SC_FIR_FAST, the explicitly named
+ * tolerance mode: multiply-adds are contracted (FFMA), results agree with the reference to ~1e-6
+ * relative instead of bit for bit, and the kernel becomes HBM-bound.  Never used by sc_rx_frames_*. */
+#define SC_FIR_FAST 0x2
 int sc_fir_batch_dev(int device, int64_t n_streams, int wide, float *memory, float *sample,
                      int64_t sample_stride, int length, void *stream);
 

@@ -554,8 +554,8 @@ extern "C" int sc_fir_batch_dev(int device, int64_t n_streams, int wide, float *
     int rc = stage_device(device);
     if (rc != SC_OK) return rc;
     if (n_streams == 0 || length == 0) return SC_OK;
-    CU(launch_fir_batch(wide != 0, n_streams, (float2 *) memory, (float2 *) sample, sample_stride, length,
-                        (cudaStream_t) stream));
+    CU(launch_fir_batch((wide & 1) != 0, n_streams, (float2 *) memory, (float2 *) sample, sample_stride, length,
+                        (cudaStream_t) stream, (wide & SC_FIR_FAST) != 0));
     return SC_OK;
 }
 

@@ -24,7 +24,7 @@ cudaError_t launch_track(bool debug_eq, const float2 *win, const int *max_index,
 
 // sc_stage_kernels.cu
 cudaError_t launch_fir_batch(bool wide, long n_streams, float2 *memory, float2 *sample, long sample_stride,
-                             int length, cudaStream_t st);
+                             int length, cudaStream_t st, bool fast = false);
 cudaError_t launch_search_batch(long n_streams, const float2 *symbols, long symbol_stride, int *max_index,
                                 float *max_value, cudaStream_t st);
 cudaError_t launch_track_window_batch(long n_streams, const float2 *symbols, long symbol_stride,

@@ -14,71 +14,86 @@ namespace sc {
 
 // ------------------------------------------------------------------------------------------------
 // fir(): 49-tap real-coefficient FIR on complex samples, in place, caller-owned delay line holding
-// the RAW past inputs, output scaled by GAIN.  One CTA per stream walks the samples in tiles of
-// 640 (128 threads x 5 consecutive outputs; lane stride 5 slots => conflict-free) with the last
-// 49 raw inputs carried in shared memory between tiles, so each sample is read and written once.
+// the RAW past inputs, output scaled by GAIN.  One WARP per stream walks the samples in tiles of
+// 160 (32 lanes x 5 consecutive outputs; lane stride 5 slots => conflict-free LDS.64) with the last
+// 49 raw inputs carried in shared memory between tiles, so each sample is read and written once and
+// only __syncwarp() is needed; 32 warps per SM hide the global-memory latency of each other's tiles.
 // ext[0..48] = memory[0..48] (oldest first), ext[49 + j] = sample[j];
 // out[j] = GAIN * sum_k ext[j + 1 + k] * coeff[k], k ascending (src/fir.c:36-42).
+//
+// FAST = true is the explicitly named tolerance mode (SC_FIR_FAST): the multiply-add is contracted
+// into one FFMA2, which halves the FP32 work, at the price of last-bit differences from the
+// reference (never used on the parity path).
 // ------------------------------------------------------------------------------------------------
-constexpr int FIR_THREADS = 128;
+constexpr int FIR_WARPS = 8;
 constexpr int FIR_R = 5;
-constexpr int FIR_TILE = FIR_THREADS * FIR_R;          // 640
+constexpr int FIR_TILE = 32 * FIR_R;                   // 160
 
-template <bool WIDE>
-__global__ void __launch_bounds__(FIR_THREADS)
+template <bool WIDE, bool FAST>
+__global__ void __launch_bounds__(FIR_WARPS * 32, 4)
 fir_batch_kernel(float2 *__restrict__ memory, float2 *__restrict__ sample, long sample_stride, int length,
                  long n_streams) {
-    __shared__ __align__(16) float2 ext[NTAPS + FIR_TILE + 8];
-    __shared__ float2 carry[NTAPS];
-    const int t = threadIdx.x;
-    for (long s = blockIdx.x; s < n_streams; s += gridDim.x) {
+    __shared__ __align__(16) float2 ext_all[FIR_WARPS][NTAPS + FIR_TILE + 7];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2 *ext = ext_all[warp];
+    for (long s = (long) blockIdx.x * FIR_WARPS + warp; s < n_streams; s += (long) gridDim.x * FIR_WARPS) {
         float2 *mem = memory + s * NTAPS;
         float2 *x = sample + s * sample_stride;
-        if (t < NTAPS) ext[t] = mem[t];
-        __syncthreads();
+        __syncwarp();
+        for (int i = lane; i < NTAPS; i += 32) ext[i] = mem[i];
         for (int t0 = 0; t0 < length; t0 += FIR_TILE) {
             const int n = min(FIR_TILE, length - t0);
-            for (int j = t; j < n; j += FIR_THREADS) ext[NTAPS + j] = x[t0 + j];
-            __syncthreads();
+            for (int j = lane; j < n; j += 32) ext[NTAPS + j] = x[t0 + j];
+            __syncwarp();
             u64 acc[FIR_R];
 #pragma unroll
             for (int r = 0; r < FIR_R; r++) acc[r] = 0ull;
-            if (FIR_R * t < n) {
-                const u64 *ep = reinterpret_cast<const u64 *>(ext) + FIR_R * t + 1;
+            if (FIR_R * lane < n) {
+                const u64 *ep = reinterpret_cast<const u64 *>(ext) + FIR_R * lane + 1;
 #pragma unroll
                 for (int j = 0; j < NTAPS + FIR_R - 1; j++) {
                     const u64 v = ep[j];
 #pragma unroll
                     for (int r = 0; r < FIR_R; r++) {
                         const int k = j - r;
-                        if (k >= 0 && k < NTAPS) acc[r] = pk_add(acc[r], pk_mul_bcast_pz(v, tap<WIDE>(k)));
+                        if (k >= 0 && k < NTAPS) {
+                            if (FAST) acc[r] = pk_fma_bcast(v, tap<WIDE>(k), acc[r]);
+                            else acc[r] = pk_add(acc[r], pk_mul_bcast_pz(v, tap<WIDE>(k)));
+                        }
                     }
                 }
             }
-            if (t < NTAPS) carry[t] = ext[n + t];      // the last 49 raw inputs
-            __syncthreads();
+            // the last 49 raw inputs become the head of the next tile
+            float2 c0 = make_float2(0.f, 0.f), c1 = c0;
+            c0 = ext[n + lane];
+            if (lane + 32 < NTAPS) c1 = ext[n + lane + 32];
+            __syncwarp();
 #pragma unroll
             for (int r = 0; r < FIR_R; r++) {
-                const int j = FIR_R * t + r;
+                const int j = FIR_R * lane + r;
                 if (j < n) {
                     float yr, yi;
                     unpk(acc[r], yr, yi);
                     x[t0 + j] = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));
                 }
             }
-            if (t < NTAPS) ext[t] = carry[t];
-            __syncthreads();
+            ext[lane] = c0;
+            if (lane + 32 < NTAPS) ext[lane + 32] = c1;
+            __syncwarp();
         }
-        if (t < NTAPS) mem[t] = ext[t];
-        __syncthreads();
+        for (int i = lane; i < NTAPS; i += 32) mem[i] = ext[i];
     }
 }
 
 cudaError_t launch_fir_batch(bool wide, long n_streams, float2 *memory, float2 *sample, long sample_stride,
-                             int length, cudaStream_t st) {
-    const int grid = (int) std::min<long>(n_streams, 148L * 16);
-    if (wide) fir_batch_kernel<true><<<grid, FIR_THREADS, 0, st>>>(memory, sample, sample_stride, length, n_streams);
-    else fir_batch_kernel<false><<<grid, FIR_THREADS, 0, st>>>(memory, sample, sample_stride, length, n_streams);
+                             int length, cudaStream_t st, bool fast) {
+    const int grid = (int) std::min<long>((n_streams + FIR_WARPS - 1) / FIR_WARPS, 148L * 4);
+    const int thr = FIR_WARPS * 32;
+    if (fast) {
+        if (wide) fir_batch_kernel<true, true><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams);
+        else fir_batch_kernel<false, true><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams);
+    } else if (wide) fir_batch_kernel<true, false><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams);
+    else fir_batch_kernel<false, false><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams);
     g_launch_count++;
     return cudaGetLastError();
 }

@@ -229,3 +229,24 @@ def test_branch_free_reciprocal_is_correctly_rounded(sc):
     sc._lib.check(sc.lib.sc_selftest_rcp_dev(0, lo, hi, bad.data_ptr(), 0))
     torch.cuda.synchronize()
     assert hi - lo > 2_000_000_000 and int(bad.item()) == 0
+
+
+def test_fir_fast_mode_is_tolerance_parity_only(sc, oracle):
+    """SC_FIR_FAST (contracted multiply-adds): agrees with the reference to 1e-5 relative, not bit for bit."""
+    import torch
+    rng = np.random.default_rng(31)
+    ns, length = 7, 3000
+    mem0 = (rng.normal(size=(ns, 49)) + 1j * rng.normal(size=(ns, 49))).astype(np.complex64)
+    x0 = (rng.normal(size=(ns, length)) + 1j * rng.normal(size=(ns, length))).astype(np.complex64)
+    dm, dx = dev(mem0.view(np.float32)), dev(x0.view(np.float32))
+    sc._lib.check(sc.lib.sc_fir_batch_dev(0, ns, 2, dm.data_ptr(), dx.data_ptr(), length, length, 0))
+    torch.cuda.synchronize()
+    y = c64_to_f32(dx)
+    exact = x0.copy()
+    for s in range(ns):
+        m = mem0[s].copy()
+        oracle.fir(m, False, exact[s])
+        assert np.array_equal(c64_to_f32(dm)[s].view(np.uint32), m.view(np.uint32))       # the delay line holds raw inputs
+    scale = np.abs(exact).max()
+    assert np.abs(y - exact).max() <= 1e-5 * scale                                         # tolerance stated: 1e-5 relative
+    assert not np.array_equal(y.view(np.uint32), exact.view(np.uint32))                    # and it really is a different rounding
