@@ -67,6 +67,10 @@ class ModemBank:
         self.device = device
         self.debug_eq = debug_eq
 
+    @staticmethod
+    def result_dtype() -> np.dtype:
+        return RESULT_DTYPE
+
     def close(self) -> None:
         if self._h:
             lib.sc_destroy(self._h)
