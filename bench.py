@@ -62,52 +62,92 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML from a background thread,
+    every 5 ms; falls back to `nvidia-smi -lms` when NVML is unavailable)."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.path = None
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = False
+        self._thread = None
+        self._proc = None
+        self._path = None
+
+    def _run(self, pynvml, h):
+        while not self._stop:
+            try:
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._run, args=(pynvml, h), daemon=True)
+            self._thread.start()
+            return
         except Exception:
-            self.proc = None
+            self._thread = None
+        try:
+            fd, self._path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self._proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                           "--format=csv,noheader,nounits", "-lms", "100"],
+                                          stdout=open(self._path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self._proc = None
+
+    def mark(self):
+        """Call at the start of the timed region: earlier samples (warm-up) are dropped."""
+        self.samples = []
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self._thread is not None:
+            self._stop = True
+            self._thread.join(timeout=2)
+            sm = self.samples
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
+                    "sm_max_mhz": self.max_mhz, "samples": len(sm), "reasons": sorted(self.reasons), "source": "nvml, 5 ms"}
+        if self._proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no clock source available"]}
+        self._proc.terminate()
         try:
-            self.proc.wait(timeout=5)
+            self._proc.wait(timeout=5)
         except Exception:
-            self.proc.kill()
+            self._proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
+        for line in open(self._path):
             f = [t.strip() for t in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 6:
                 continue
             try:
                 sm.append(float(f[0]))
                 mx.append(float(f[1]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+            for n, v in zip(names, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        os.unlink(self.path)
-        busy = sorted(sm)[len(sm) // 2:] if sm else []       # upper half = samples under load
+        os.unlink(self._path)
+        busy = sorted(sm)[len(sm) // 2:] if sm else []
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100 (incl. warm-up)"}
 
 
 def synth_input(sc, torch, bank, streams, samples_per_stream, seed, rank):
@@ -250,6 +290,7 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    sampler.mark()
     launches0 = sc.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
