@@ -35,18 +35,25 @@ def test_no_contracted_fma_in_exact_kernels():
     assert any("sm_100a" in x or True for x in funcs)
     seen = 0
     for name, ins in funcs.items():
-        if not any(k in name for k in ("frontend_kernel", "fir_batch_kernel", "search_batch_kernel")):
+        if not any(k in name for k in ("frontend_kernel", "fir_batch_kernel")):
+            continue
+        if re.search(r"fir_batch_kernelILb[01]ELb1E", name):
+            # the explicitly named tolerance mode (SC_FIR_FAST) is the one place where contraction is wanted
+            assert any("FFMA2" in i and not i.rstrip(" ;").endswith(("RZ", "RZ.F32")) for i in ins), name
             continue
         seen += 1
         packed = [i for i in ins if "FFMA2" in i]
-        if "search" not in name:
-            assert len(packed) > 200, name
+        assert len(packed) > 200, name
         for i in packed:
             assert re.search(r",\s*RZ(\.F32)?\s*;?$", i.rstrip(" ;") + ";") or i.rstrip(" ;").endswith("RZ.F32") \
                 or i.rstrip(" ;").endswith("RZ"), (name, i)
         assert sum("FADD2" in i for i in ins) >= len(packed)
         assert not [i for i in ins if re.match(r"(@!?P\d+\s+)?FFMA\b", i)], name      # no scalar FFMA at all here
     assert seen >= 4
+    for name, ins in funcs.items():
+        if "search_batch_kernel" in name:                      # pure adds: no multiply-add of any kind
+            assert not [i for i in ins if "FFMA" in i], name
+            assert sum(bool(re.match(r"(@!?P\d+\s+)?FADD\b", i)) for i in ins) >= 1024
     for name, ins in funcs.items():
         if "track_kernel" in name or "track_window_kernel" in name:
             # 5 reciprocals per step x 2 loops (+ slow paths); anything beyond that would be a contraction
