@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <tuple>
 #include <mutex>
@@ -21,7 +22,7 @@
 #include "sc_common.cuh"
 
 namespace sc {
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 }
 
 using namespace sc;
@@ -59,6 +60,7 @@ struct sc_modem {
 
     // per-stream device state
     int *timing[2] = {nullptr, nullptr};    // rx_timing at entry of call n in timing[n & 1]
+    int *timing_cold = nullptr;             // FINE_TIMING_OFFSET for every stream (source of resets)
     float2 *win = nullptr;                  // tracker windows, tiles of 32 streams x WIN_ROWS
     int *max_index = nullptr;
     float *max_value = nullptr;
@@ -131,15 +133,15 @@ static int modem_cold(sc_modem *m) {
     const int64_t np = m->n_pad;
     // rx_timing = FINE_TIMING_OFFSET (qpsk.c:53); windows of calls 0 and 1 are the zero-initialised
     // decimated_frame (qpsk.c:42), whose search gives max_index 0 / max_value 0.0
-    std::vector<int> t(np, 3);
-    CU(cudaMemcpy(m->timing[0], t.data(), np * sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(m->timing[1], t.data(), np * sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemset(m->win, 0, (size_t) (np / 32) * WIN_ROWS * 32 * sizeof(float2)));
-    CU(cudaMemset(m->max_index, 0, np * sizeof(int)));
-    CU(cudaMemset(m->max_value, 0, np * sizeof(float)));
-    CU(cudaMemset(m->hist, 0, (size_t) m->n * FRAME * sizeof(int16_t)));
+    // (hist needs no reset: it is only read by a batch that continues a previous one, which saved it)
+    CU(cudaMemcpyAsync(m->timing[0], m->timing_cold, np * sizeof(int), cudaMemcpyDeviceToDevice, m->pipe[0]));
+    CU(cudaMemcpyAsync(m->timing[1], m->timing_cold, np * sizeof(int), cudaMemcpyDeviceToDevice, m->pipe[0]));
+    CU(cudaMemsetAsync(m->win, 0, (size_t) (np / 32) * WIN_ROWS * 32 * sizeof(float2), m->pipe[0]));
+    CU(cudaMemsetAsync(m->max_index, 0, np * sizeof(int), m->pipe[0]));
+    CU(cudaMemsetAsync(m->max_value, 0, np * sizeof(float), m->pipe[0]));
     const float2 one = make_float2(1.0f, 0.0f);                         // cmplx(0.0f), qpsk.c:427
-    CU(cudaMemcpy(m->rx_phase, &one, sizeof one, cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(m->rx_phase, &one, sizeof one, cudaMemcpyHostToDevice, m->pipe[0]));
+    CU(cudaStreamSynchronize(m->pipe[0]));
     m->call = 0;
     m->lfsr_rx = 0x4A80;
     return SC_OK;
@@ -172,10 +174,16 @@ extern "C" int sc_create(sc_modem **out, int device, int64_t n_streams, uint32_t
         const int64_t np = m->n_pad;
         CU(cudaMalloc(&m->timing[0], np * sizeof(int)));
         CU(cudaMalloc(&m->timing[1], np * sizeof(int)));
+        CU(cudaMalloc(&m->timing_cold, np * sizeof(int)));
+        {
+            std::vector<int> t(np, 3);
+            CU(cudaMemcpy(m->timing_cold, t.data(), np * sizeof(int), cudaMemcpyHostToDevice));
+        }
         CU(cudaMalloc(&m->win, (size_t) (np / 32) * WIN_ROWS * 32 * sizeof(float2)));
         CU(cudaMalloc(&m->max_index, np * sizeof(int)));
         CU(cudaMalloc(&m->max_value, np * sizeof(float)));
         CU(cudaMalloc(&m->hist, (size_t) m->n * FRAME * sizeof(int16_t)));
+        CU(cudaMemset(m->hist, 0, (size_t) m->n * FRAME * sizeof(int16_t)));
         CU(cudaMalloc(&m->rx_phase, sizeof(float2)));
         for (int i = 0; i < N_PIPE; i++) {
             CU(cudaStreamCreateWithFlags(&m->pipe[i], cudaStreamNonBlocking));
@@ -199,6 +207,9 @@ extern "C" void sc_destroy(sc_modem *m) {
     cudaDeviceSynchronize();
     cudaFree(m->timing[0]);
     cudaFree(m->timing[1]);
+    cudaFree(m->timing_cold);
+    for (cudaEvent_t e : m->ev_fe) cudaEventDestroy(e);
+    for (cudaEvent_t e : m->ev_tk) cudaEventDestroy(e);
     cudaFree(m->win);
     cudaFree(m->max_index);
     cudaFree(m->max_value);
@@ -221,7 +232,7 @@ extern "C" void sc_destroy(sc_modem *m) {
 extern "C" int sc_reset(sc_modem *m) {
     if (!m) return fail(SC_EINVAL, "sc_reset: null handle");
     CU(cudaSetDevice(m->device));
-    CU(cudaDeviceSynchronize());
+    for (int i = 0; i < N_PIPE; i++) CU(cudaStreamSynchronize(m->pipe[i]));
     return modem_cold(m);
 }
 

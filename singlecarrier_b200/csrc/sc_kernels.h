@@ -4,12 +4,13 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "../../include/singlecarrier_b200.h"
 
 namespace sc {
 
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;
 
 // sc_rx_kernels.cu
 cudaError_t launch_nco_table(float2 *phase_state, float2 rect, const int *seg_len, int n_seg, float scale,

@@ -312,7 +312,6 @@ track_kernel(const float2 *__restrict__ win, const int *__restrict__ max_index, 
 // ------------------------------------------------------------------------------------------------
 // host-side launchers (called from sc_api.cu)
 // ------------------------------------------------------------------------------------------------
-extern unsigned long long g_launch_count;
 
 cudaError_t launch_nco_table(float2 *phase_state, float2 rect, const int *seg_len, int n_seg, float scale,
                              float2 *out, cudaStream_t st) {
