@@ -104,7 +104,8 @@ int  sc_profile_read(sc_modem *m, double out[4]);
  *       everything already queued on `stream` (a cudaStream_t) and `stream` waits for it.
  * _host: all pointers are host pointers (pinned gives asynchronous copies); host->device
  *        copies of the samples and device->host copies of the results are pipelined with the
- *        kernels in slabs of streams; returns after everything has landed.
+ *        kernels in slabs of streams; returns after everything has landed.  Only samples
+ *        80..1703 of each frame are transferred: no other sample can influence any output.
  */
 int sc_rx_frames_dev(sc_modem *m, const int16_t *in, int64_t stream_stride, int n_frames,
                      sc_frame_result *results, int64_t result_stride, float *eq_dbg, void *stream);
