@@ -9,9 +9,9 @@ __device__ __forceinline__ u64 pk_mulz(u64 a, u64 b){ u64 r; const u64 z=0; asm 
 __device__ __forceinline__ u64 pk_fma(u64 a, u64 b, u64 c){ u64 r; asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 template<int OP> __global__ void k(float* out, long long* cyc, float seed, int iters){
-  float a[8]; u64 p[8];
+  float a[8], b[8]; u64 p[8], q[8];
   #pragma unroll
-  for(int i=0;i<8;i++){ a[i]=seed+i+threadIdx.x; p[i]=((u64)__float_as_uint(a[i])<<32)|__float_as_uint(a[i]*0.5f); }
+  for(int i=0;i<8;i++){ a[i]=seed+i+threadIdx.x; b[i]=a[i]*0.25f; q[i]=((u64)__float_as_uint(a[i]*0.3f)<<32)|__float_as_uint(a[i]*0.7f); p[i]=((u64)__float_as_uint(a[i])<<32)|__float_as_uint(a[i]*0.5f); }
   float c = seed*0.999f; u64 pc = ((u64)__float_as_uint(c)<<32)|__float_as_uint(c);
   long long t0 = clock64();
   for(int it=0; it<iters; it++){
@@ -29,13 +29,17 @@ template<int OP> __global__ void k(float* out, long long* cyc, float seed, int i
         if(OP==7){ a[i]=__fmul_rn(a[i],c); a[i]=__fadd_rn(a[i],c);}          // 2 instr
         if(OP==8){ u64 t=pk_mulz(p[i],pc); p[i]=pk_add(p[(i+1)&7],t);}       // 2 instr
         if(OP==9){ a[i]=__fsub_rn(__fmul_rn(a[i],c), __fmul_rn(a[(i+1)&7],c)); } // 3 instr
+        if(OP==10){ p[i]=pk_add(p[i],pc); a[i]=__fadd_rn(a[i],c); }          // 1 packed + 1 scalar
+        if(OP==11){ p[i]=pk_add(p[i],pc); a[i]=__fadd_rn(a[i],c); b[i]=__fadd_rn(b[i],c); }  // 1 packed + 2 scalar
+        if(OP==12){ p[i]=pk_mulz(p[i],pc); a[i]=__fmul_rn(a[i],c); b[i]=__fadd_rn(b[i],c); }
+        if(OP==13){ p[i]=pk_add(p[i],pc); q[i]=pk_mulz(q[i],pc); a[i]=__fadd_rn(a[i],c); b[i]=__fmul_rn(b[i],c);}  // 2 packed + 2 scalar
       }
     }
   }
   long long t1 = clock64();
   float s=0; 
   #pragma unroll
-  for(int i=0;i<8;i++){ s+=a[i]+__uint_as_float((unsigned)p[i])+__uint_as_float((unsigned)(p[i]>>32)); }
+  for(int i=0;i<8;i++){ s+=b[i]+__uint_as_float((unsigned)q[i])+__uint_as_float((unsigned)(q[i]>>32))+a[i]+__uint_as_float((unsigned)p[i])+__uint_as_float((unsigned)(p[i]>>32)); }
   out[blockIdx.x*blockDim.x+threadIdx.x]=s;
   if(threadIdx.x==0) cyc[blockIdx.x]=t1-t0;
 }
@@ -53,6 +57,7 @@ template<int OP> void run(const char* name, int per){
 int main(){
   run<0>("FADD reg",1); run<1>("FMUL reg",1); run<2>("FMUL imm",1); run<3>("FFMA reg",1);
   run<4>("FADD2",1); run<5>("FFMA2 (mul, +0)",1); run<6>("FFMA2 full",1);
+  run<10>("FADD2 + FADD",2); run<11>("FADD2 + 2 FADD",3); run<12>("FFMA2z + FMUL + FADD",3); run<13>("FADD2+FFMA2z+FADD+FMUL",4);
   run<7>("FMUL+FADD pair",2); run<8>("FFMA2z+FADD2 pair",2); run<9>("2FMUL+FSUB",3);
   return 0;
 }
