@@ -1,0 +1,20 @@
+#!/bin/bash
+# Typical B200 session (run through gpurun): parity tests, benchmark, then the ncu captures that
+# tools/profile_summary.py turns into profiles/rNN_*.md.  Usage: bash tools/gpu_session.sh r01
+set -x
+R=${1:-r01}
+mkdir -p gpurun_out
+python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null > gpurun_out/bench_ref_$R.json
+python bench.py 2>gpurun_out/bench.err > gpurun_out/bench_$R.json
+python tools/stage_bench.py 2>&1 | tail -8 > gpurun_out/stage_bench_$R.md
+# launch list (every launch with its device time; compare shares)
+CMD="python bench.py --streams 131072 --seconds 2 --steps 2 --warmup 3 --no-e2e --no-cpu"
+$CMD > gpurun_out/plain_$R.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$R.csv $CMD > gpurun_out/ncu_list.log 2>&1
+# full capture of the two RX kernels at full launch size (one slab)
+CMD2="python bench.py --streams 131072 --seconds 1 --steps 1 --warmup 3 --no-e2e --no-cpu --slab-parts 1"
+$CMD2 > gpurun_out/plain2_$R.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'frontend_kernel|track_kernel' -s 10 -c 2 -o gpurun_out/prof_$R $CMD2 > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log
