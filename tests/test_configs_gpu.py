@@ -109,3 +109,30 @@ def test_host_entry_point_matches_device_entry_point_large(sc):
     host, _ = bank.rx_frames_host(wl.samples.cpu().numpy(), nf)
     assert host.tobytes() == res.tobytes()
     bank.close()
+
+
+def test_config4_per_gpu_shard_131072_streams_10s(sc, oracle):
+    """bench.py's workload (config 4 sharded: 131,072 streams x 42 calls, 21 GB of samples): oracle on a
+    1,024-stream subset, results independent of the slab split, counters consistent."""
+    import torch
+    from singlecarrier_b200 import harness
+    from singlecarrier_b200.modem import OPT_SLAB_PARTS
+    ns, nf = 131072, 42
+    bank = sc.ModemBank(ns)
+    wl = harness.synthesize(bank, 80000, seed=0x5C0DE5, config=4)
+    res = harness.demodulate(bank, wl.samples, nf)
+    bank.set_option(OPT_SLAB_PARTS, 5)                                         # a different partition of the bank
+    res5 = harness.demodulate(bank, wl.samples, nf)
+    assert torch.equal(res, res5)
+    bank.set_option(OPT_SLAB_PARTS, 0)
+    rng = np.random.default_rng(4)
+    idx = np.sort(rng.choice(ns, 1024, replace=False))
+    check_subset(sc, oracle, wl, res, nf, idx)
+    st = harness.ber_and_lock(res, nf, wl)
+    cnt = torch.zeros(16, dtype=torch.int64, device="cuda")
+    bank.lock_stats(res, nf, cnt)
+    torch.cuda.synchronize()
+    c = cnt.cpu().numpy()
+    assert c[0] == ns * nf and c[1] == st["valid"][0] + int((res.view(ns, nf, 32)[:, :2, 22] != 0).sum())
+    assert st["valid"][0] > 50000                                              # ~2 % of the calls after the first two lock
+    bank.close()
