@@ -145,9 +145,15 @@ def test_track_decide_batch_vs_oracle_frames(sc, oracle):
             assert np.array_equal(sc.unpack_bits(res_all[i:i + 1])[0], bits)
 
 
-@pytest.mark.parametrize("n", [8, 64, 256, 1024, 60, 100])
+FFT_SIZES = [2, 3, 4, 5, 6, 7, 8, 11, 16, 30, 49, 60, 64, 100, 125, 128, 243, 256, 512, 1024, 2048]
+
+
+@pytest.mark.parametrize("n", FFT_SIZES)
 def test_fft_batch_matches_reference_fft(sc, gold, n):
-    """fft.h: same factorisation/butterflies/twiddles as src/fft.c => bit-identical."""
+    """fft.h: same factorisation/butterflies/twiddles as src/fft.c => bit-identical, for
+    radix 4, 2, 3, 5 and generic (7, 11) stages.  The reference's radix-5 butterfly (src/fft.c:324-334) does
+    not compute a DFT (relative error ~1 against the definition for every length with a factor 5); it is
+    mirrored as written, so the DFT-definition check below only runs for lengths without that factor."""
     import torch
     g = gold("fft_golden.npz")
     x = g[f"c{n}_in"]
@@ -160,14 +166,13 @@ def test_fft_batch_matches_reference_fft(sc, gold, n):
         y = c64_to_f32(d_out)
         ref = g[f"c{n}_{inv}"]
         assert np.array_equal(y[0].view(np.uint32), ref.view(np.uint32)), (n, inv, np.abs(y[0] - ref).max())
-        # independent check against the DFT definition in float64 (radix 4/2 sizes; the reference's
-        # radix-5 butterfly is mirrored as written)
-        if n in (8, 64, 256, 1024):
+        # independent check against the DFT definition in float64
+        if n % 5 != 0:
             want = np.fft.ifft(batch.astype(np.complex128), axis=1) * n if inv else np.fft.fft(batch.astype(np.complex128), axis=1)
-            assert np.abs(y - want).max() <= 1e-5 * np.abs(want).max() * np.log2(n)
+            assert np.abs(y - want).max() <= 1e-5 * np.abs(want).max() * max(1.0, np.log2(n))
 
 
-@pytest.mark.parametrize("n", [64, 256])
+@pytest.mark.parametrize("n", [6, 20, 64, 250, 256])
 def test_fftr_fftri_match_reference(sc, gold, n):
     import torch
     g = gold("fft_golden.npz")
@@ -180,7 +185,8 @@ def test_fftr_fftri_match_reference(sc, gold, n):
     torch.cuda.synchronize()
     assert np.array_equal(c64_to_f32(d_spec).view(np.uint32), g[f"r{n}_spec"].view(np.uint32))
     assert np.array_equal(d_back.cpu().numpy().view(np.uint32), g[f"r{n}_back"].view(np.uint32))
-    assert np.abs(d_back.cpu().numpy() / n - xr).max() < 1e-5
+    if n % 5 != 0:
+        assert np.abs(d_back.cpu().numpy() / n - xr).max() < 1e-5
 
 
 def test_large_fft_uses_global_scratch(sc):

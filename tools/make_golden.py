@@ -129,7 +129,7 @@ def main():
     L.encode_fftr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.encode_fftri.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     f = {}
-    for n in (8, 64, 256, 1024, 60, 100):
+    for n in (2, 3, 4, 5, 6, 7, 8, 11, 16, 30, 49, 60, 64, 100, 125, 128, 243, 256, 512, 1024, 2048):
         xin = (rng.normal(size=n) + 1j * rng.normal(size=n)).astype(np.complex64)
         for inv in (0, 1):
             cfg_ = L.fft_alloc(n, inv, None, None)
@@ -137,7 +137,7 @@ def main():
             L.fft(cfg_, xin.ctypes.data, out.ctypes.data)
             f[f"c{n}_{inv}"] = out
         f[f"c{n}_in"] = xin
-    for n in (64, 256):
+    for n in (6, 20, 64, 250, 256):
         xr = rng.normal(size=n).astype(np.float32)
         cf = L.fftr_alloc(n, 0, None, None)
         spec = np.zeros(n // 2 + 1, np.complex64)
