@@ -177,3 +177,50 @@ def test_argument_validation(sc):
     assert bank.call_index == 0
     assert L.sc_fft_batch_dev(0, 1, 0, 0, x.ctypes.data, x.ctypes.data, None) == -1
     bank.close()
+
+
+def test_long_run_many_small_batches(sc, oracle):
+    """120 calls (> 1 minute of audio) fed in uneven batches: the NCO phasor table, its per-frame
+    renormalisation and the scrambler position must carry across API calls exactly."""
+    rng = np.random.default_rng(14)
+    nf, ns = 120, 5
+    samples = synth_streams(oracle, rng, ns, nf, noise_levels=(0.0, 200.0, 2000.0))
+    bank = sc.ModemBank(ns, debug_eq=True)
+    parts, eqs, a = [], [], 0
+    sizes = [1, 2, 3, 7, 1, 13, 29, 5, 11, 48]
+    assert sum(sizes) == nf
+    for n in sizes:
+        r, e = bank.rx_frames_host(np.ascontiguousarray(samples[:, a * 1880:(a + n) * 1880]), n)
+        parts.append(r)
+        eqs.append(e)
+        a += n
+    assert bank.call_index == nf
+    bank.close()
+    res, eq = np.concatenate(parts, axis=1), np.concatenate(eqs, axis=1)
+    obits, ostats = oracle_results(oracle, samples, nf)
+    assert compare_results(res, eq, obits, ostats) == []
+    assert (res["call_index"] == np.arange(nf)[None, :]).all()
+    assert ostats["valid"][:, 2:].sum() > 20
+
+
+def test_nco_table_matches_reference_recurrence(sc, oracle):
+    """The device-generated RX/TX phasor tables against a float32 re-run of the reference's recurrence
+    (cmul per sample, cabsf renormalisation per frame), bit for bit over 60 frames."""
+    import ctypes as C
+    libm = C.CDLL("libm.so.6")
+    libm.hypotf.restype = C.c_float
+    libm.hypotf.argtypes = [C.c_float, C.c_float]
+    bank = sc.ModemBank(1)
+    tab = bank.nco_table(0, 60)
+    bank.close()
+    r = oracle.nco_rect(-1100.0)
+    rr, ri = np.float32(r.real), np.float32(r.imag)
+    pr, pi = np.float32(1), np.float32(0)
+    want = np.zeros((60, 1880), np.complex64)
+    for f in range(60):
+        for i in range(1880):
+            pr, pi = np.float32(np.float32(pr * rr) - np.float32(pi * ri)), np.float32(np.float32(pr * ri) + np.float32(pi * rr))
+            want[f, i] = pr + 1j * pi
+        m = np.float32(libm.hypotf(float(pr), float(pi)))
+        pr, pi = np.float32(pr / m), np.float32(pi / m)
+    assert np.array_equal(tab.view(np.uint32), want.view(np.uint32))
