@@ -142,3 +142,26 @@ def test_legacy_tx_frame_arbitrary_symbols(oracle):
         oracle.lib.sco_tx_frame(st.ctypes.data, y.ctypes.data, sym.ctypes.data, n, int(pre))
         want.append(y)
     assert np.array_equal(got, np.concatenate(want))
+
+
+def test_batched_c_example(tmp_path, oracle, gold):
+    """examples/batched_demo.c: the batched C ABI driven from plain C (no Python in the loop)."""
+    exe = tmp_path / "batched_demo"
+    libdir = os.path.join(ROOT, "singlecarrier_b200")
+    subprocess.run(["gcc", "-std=gnu11", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "batched_demo.c"), "-o", str(exe), "-L", libdir,
+                    "-lsinglecarrier_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe), os.path.join(ROOT, "tests", "golden", "preamble_qpsk_8k.raw"), "3"], check=True,
+                         capture_output=True, text=True, timeout=300).stdout.strip().splitlines()
+    x = gold("preamble_qpsk_8k.raw")
+    nf = (x.size + 3) // 1880 + 2
+    want = []
+    for k in range(3):
+        s = np.zeros(nf * 1880, np.int16)
+        s[k:k + x.size] = x
+        bits, st = oracle.run_stream(s)
+        for n in range(nf):
+            if st["valid"][n]:
+                want.append(f"stream {k} call {n} matches {st['matches'][n]} max_index {st['max_index'][n]} "
+                            f"max_value {st['max_value'][n]:.2f} bits " + "".join(map(str, bits[n])))
+    assert out[:-1] == want and out[-1].startswith(f"3 streams x {nf} calls")
