@@ -340,6 +340,9 @@ def main():
     dom, other = (tk, fe) if tk_ms >= fe_ms else (fe, tk)
     roofline = dict(dom)
     roofline["peak_source"] = peak_src
+    roofline["timing"] = ("CUDA events around every launch, on the launching stream, in one extra single-slab pass over the "
+                          "same input right after the timed steps (the timed steps run two slabs on two streams, whose "
+                          "launches overlap and cannot be timed individually)")
     roofline["other_kernel"] = other
     chain_gbs = streams * n_frames * CHAIN_BYTES * args.steps / (ms_total * 1e-3) / 1e9
     roofline["chain"] = {"bytes_per_symbol": CHAIN_BYTES / SYM_PER_FRAME, "achieved_gbs": chain_gbs,
