@@ -13,6 +13,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # a fresh checkout has no built artefacts: build the C-ABI library (nvcc cross-compiles without a GPU)
+    # and the oracle once, exactly as __graft_entry__.build() does
+    lib = os.path.join(ROOT, "singlecarrier_b200", "libsinglecarrier_b200.so")
+    if not os.path.exists(lib) or not os.path.exists(os.path.join(ROOT, "oracle", "libsc_oracle.so")):
+        import subprocess
+        subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.build()"], cwd=ROOT, check=True,
+                       stdout=subprocess.DEVNULL)
 
 
 @pytest.fixture(scope="session")
