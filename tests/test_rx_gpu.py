@@ -224,3 +224,20 @@ def test_nco_table_matches_reference_recurrence(sc, oracle):
         m = np.float32(libm.hypotf(float(pr), float(pi)))
         pr, pi = np.float32(pr / m), np.float32(pi / m)
     assert np.array_equal(tab.view(np.uint32), want.view(np.uint32))
+
+
+def test_create_destroy_does_not_leak_device_memory(sc):
+    import torch
+    torch.cuda.synchronize()
+    x = np.zeros((4096, 3 * 1880), np.int16)
+    for k in range(3):                                      # warm the allocator / library state
+        b = sc.ModemBank(4096, debug_eq=True)
+        b.rx_frames_host(x, 3)
+        b.close()
+    free0, _ = torch.cuda.mem_get_info()
+    for k in range(25):
+        b = sc.ModemBank(4096, debug_eq=(k % 2 == 0))
+        b.rx_frames_host(x, 3)
+        b.close()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 64 << 20
