@@ -234,7 +234,7 @@ def main():
     ap.add_argument("--seconds", type=int, default=10, help="seconds of 8 kHz audio per stream")
     ap.add_argument("--seed", type=int, default=0x5C0DE5)
     ap.add_argument("--ref-streams", type=int, default=4096, help="streams per step of the CPU reference arm")
-    ap.add_argument("--cpu-streams", type=int, default=2048, help="streams of the cpu_baseline sample")
+    ap.add_argument("--cpu-streams", type=int, default=4096, help="streams of the cpu_baseline sample")
     ap.add_argument("--slab-parts", type=int, default=0, help="override the library's slab split (0 = default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
