@@ -88,8 +88,10 @@ __device__ __forceinline__ void fe_load(uint32_t (&raw)[FE_KN], const uint32_t *
 #pragma unroll
     for (int k = 0; k < FE_KN; k++) {
         const int p = lane + 32 * (k + K_LO);
-        raw[k] = 0u;
-        if (p < FE_NPAIR && base2 + 2 * p + 1 < FRAME) raw[k] = __ldg(fp + p);
+        // base2 <= 206 and p <= 747 keep every pair inside the 1880-sample frame; only the last round
+        // of pass B runs past the 748 pairs that exist
+        if (k + K_LO == FE_PAIRS_PER_LANE - 1) raw[k] = p < FE_NPAIR ? __ldg(fp + p) : 0u;
+        else raw[k] = __ldg(fp + p);
     }
 }
 
@@ -104,7 +106,13 @@ __device__ __forceinline__ void fe_stage(float2 *__restrict__ buf, const uint32_
         const uint32_t (&raw)[FE_KN] = rawk;
         const int p = lane + 32 * k;
         const int d = 2 * p + off;                            // slot of the pair's first sample
-        if (d >= 0 && d + 1 < FE_BUF && p < FE_NPAIR) {
+        // off is +2 in pass A and -722/-724 in pass B, so only three rounds can fall outside the buffer:
+        // the last of pass A (slots >= FE_BUF), the first of pass B (slots < 0), the last of pass B (p >= 748)
+        bool ok = true;
+        if (K_LO == FE_KA_LO && k == FE_KA_HI) ok = d + 1 < FE_BUF;
+        if (K_LO == FE_KB_LO && k == FE_KB_LO) ok = d >= 0;
+        if (K_LO == FE_KB_LO && k == FE_KB_HI) ok = p < FE_NPAIR;
+        if (ok) {
             const float4 ph = __ldg(reinterpret_cast<const float4 *>(tab + 2 * p));
             const float v0 = (float) (int16_t) (raw[kk] & 0xffffu);
             const float v1 = (float) (int16_t) (raw[kk] >> 16);
@@ -133,7 +141,7 @@ __device__ __forceinline__ void fe_fir(const float2 *__restrict__ buf, int front
 }
 
 template <bool WIDE>
-__global__ void __launch_bounds__(FE_WARPS * 32, 8)
+__global__ void __launch_bounds__(FE_WARPS * 32, 6)
 frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2 *__restrict__ mix_table,
                 const int *__restrict__ timing_cur, const int *__restrict__ timing_next,
                 float2 *__restrict__ win, int *__restrict__ max_index_out, float *__restrict__ max_value_out,
@@ -162,7 +170,7 @@ frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2
     for (int k = 0; k < FE_KN; k++) raw[k] = 0u;
     if (active) {
         const int T = timing_cur[s];
-        base = T - (NTAPS - 1);                        // first sample needed; >= 80 once T >= 128
+        base = min(T, 2 * PRE - 1) - (NTAPS - 1);      // first sample needed; 80..207 once T is 128..255
         frame = in + s * stream_stride;
         fast = base >= 0 && ((((uintptr_t) frame) & 3) == 0);
         if (fast) {
