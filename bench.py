@@ -48,8 +48,8 @@ FE_OPS = 2 * 1494 + 290 * 198 + 2 * 255 + 128 * 128 * 2 + 128 * 3
 TK_OPS = 128 * 398 + 31 * 397
 # DRAM traffic per stream-frame from the ncu --set full capture (dram__bytes_read.sum + dram__bytes_write.sum
 # divided by the 131,072 stream-frames of one launch): profiles/r01_ncu_summary.md
-FE_DRAM_TRAFFIC = (403.762944e6 + 179.029504e6) / 131072
-TK_DRAM_TRAFFIC = (186.173440e6 + 7.513088e6) / 131072
+FE_DRAM_TRAFFIC = (403.761408e6 + 180.441344e6) / 131072
+TK_DRAM_TRAFFIC = (186.355712e6 + 6.135296e6) / 131072
 
 
 def peaks():

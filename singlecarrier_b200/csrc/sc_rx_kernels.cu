@@ -54,9 +54,9 @@ __global__ void nco_table_kernel(float2 *__restrict__ phase_state, float2 rect, 
 // range [T-48, T+1445] of ONE frame (T >= 128 after the first call), 1494 samples.
 //
 // The 290 outputs are produced in two passes of 145 (29 lanes x 5 consecutive outputs), so only
-// 769 mixed samples (6 KB) are staged in shared memory at a time: 25 KB per 4-warp CTA, 8 CTAs
-// = 32 warps per SM, which is what hides the latencies of the staging and epilogue phases behind
-// other warps' FIR/search arithmetic.  Lane l reads samples 25l .. 25l+68 of the pass: lane stride
+// 769 mixed samples (6 KB) are staged in shared memory at a time: 25 KB per 4-warp CTA; with 80
+// registers 6 CTAs = 24 warps are resident per SM, which is what hides the latencies of the staging
+// and epilogue phases behind other warps' FIR/search arithmetic.  Lane l reads samples 25l .. 25l+68 of the pass: lane stride
 // 25 slots (odd => conflict-free 64-bit reads), compile-time offsets, taps as immediates.
 // All global loads of a stream-frame (24 coalesced 4-byte loads per lane) are issued up front.
 // ------------------------------------------------------------------------------------------------
