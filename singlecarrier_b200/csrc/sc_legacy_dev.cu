@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -131,6 +132,15 @@ struct Legacy {
     std::mutex mu;
 } g;
 
+// device scratch that is released on every return path
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
+    operator T *() const { return p; }
+};
+
 #define LCU(call)                                                                                  \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
@@ -177,16 +187,14 @@ extern "C" int scl_fir(float *memory, int wide, float *sample, int length) {
     std::lock_guard<std::mutex> lock(g.mu);
     int rc = ensure();
     if (rc != SC_OK) return rc;
-    float2 *d_mem = nullptr, *d_x = nullptr;
-    LCU(cudaMalloc(&d_mem, NTAPS * sizeof(float2)));
-    LCU(cudaMalloc(&d_x, (size_t) length * sizeof(float2)));
+    DevBuf<float2> d_mem, d_x;
+    LCU(d_mem.alloc(NTAPS));
+    LCU(d_x.alloc((size_t) length));
     LCU(cudaMemcpy(d_mem, memory, NTAPS * sizeof(float2), cudaMemcpyHostToDevice));
     LCU(cudaMemcpy(d_x, sample, (size_t) length * sizeof(float2), cudaMemcpyHostToDevice));
     LCU(launch_fir_batch(wide != 0, 1, d_mem, d_x, length, length, 0));
     LCU(cudaMemcpy(memory, d_mem, NTAPS * sizeof(float2), cudaMemcpyDeviceToHost));
     LCU(cudaMemcpy(sample, d_x, (size_t) length * sizeof(float2), cudaMemcpyDeviceToHost));
-    cudaFree(d_mem);
-    cudaFree(d_x);
     return SC_OK;
 }
 
@@ -278,12 +286,12 @@ extern "C" int scl_tx_frame(int16_t *samples, const float *symbols, int length, 
     int rc = ensure();
     if (rc != SC_OK) return rc;
     const int n = length * CYC;
-    float2 *d_sym = nullptr, *d_sig = nullptr, *d_ph = nullptr;
-    int16_t *d_out = nullptr;
-    LCU(cudaMalloc(&d_sym, (size_t) length * sizeof(float2)));
-    LCU(cudaMalloc(&d_sig, (size_t) n * sizeof(float2)));
-    LCU(cudaMalloc(&d_ph, (size_t) n * sizeof(float2)));
-    LCU(cudaMalloc(&d_out, (size_t) n * sizeof(int16_t)));
+    DevBuf<float2> d_sym, d_sig, d_ph;
+    DevBuf<int16_t> d_out;
+    LCU(d_sym.alloc((size_t) length));
+    LCU(d_sig.alloc((size_t) n));
+    LCU(d_ph.alloc((size_t) n));
+    LCU(d_out.alloc((size_t) n));
     LCU(cudaMemcpy(d_sym, symbols, (size_t) length * sizeof(float2), cudaMemcpyHostToDevice));
     LCU(cudaMemcpy(g.d_seg, &n, sizeof n, cudaMemcpyHostToDevice));
     legacy_tx_stuff_kernel<<<(n + 255) / 256, 256>>>(d_sym, length, d_sig);
@@ -294,10 +302,6 @@ extern "C" int scl_tx_frame(int16_t *samples, const float *symbols, int length, 
     g_launch_count++;
     LCU(cudaGetLastError());
     LCU(cudaMemcpy(samples, d_out, (size_t) n * sizeof(int16_t), cudaMemcpyDeviceToHost));
-    cudaFree(d_sym);
-    cudaFree(d_sig);
-    cudaFree(d_ph);
-    cudaFree(d_out);
     return SC_OK;
 }
 
@@ -328,24 +332,19 @@ static int fft_host(int n, int inverse, int mode, const int *factors, const floa
     FftPlan plan;
     if ((rc = plan_from_factors(n, inverse, factors, &plan)) != SC_OK) return rc;
     const size_t in_c = mode == 2 ? (size_t) n + 1 : (size_t) n, out_c = mode == 1 ? (size_t) n + 1 : (size_t) n;
-    float2 *d_tw = nullptr, *d_st = nullptr, *d_in = nullptr, *d_out = nullptr, *d_scratch = nullptr;
-    LCU(cudaMalloc(&d_tw, (size_t) n * sizeof(float2)));
-    LCU(cudaMalloc(&d_in, in_c * sizeof(float2)));
-    LCU(cudaMalloc(&d_out, out_c * sizeof(float2)));
+    DevBuf<float2> d_tw, d_st, d_in, d_out, d_scratch;
+    LCU(d_tw.alloc((size_t) n));
+    LCU(d_in.alloc(in_c));
+    LCU(d_out.alloc(out_c));
     LCU(cudaMemcpy(d_tw, twiddles, (size_t) n * sizeof(float2), cudaMemcpyHostToDevice));
     LCU(cudaMemcpy(d_in, in, in_c * sizeof(float2), cudaMemcpyHostToDevice));
     if (mode != 0) {
-        LCU(cudaMalloc(&d_st, (size_t) std::max(n / 2, 1) * sizeof(float2)));
+        LCU(d_st.alloc((size_t) std::max(n / 2, 1)));
         LCU(cudaMemcpy(d_st, super_tw, (size_t) (n / 2) * sizeof(float2), cudaMemcpyHostToDevice));
     }
-    if ((size_t) 2 * n * sizeof(float2) > 64 * 1024) LCU(cudaMalloc(&d_scratch, (size_t) 2 * n * sizeof(float2)));
+    if ((size_t) 2 * n * sizeof(float2) > 64 * 1024) LCU(d_scratch.alloc((size_t) 2 * n));
     LCU(launch_fft(plan, d_tw, d_st, mode, d_in, d_out, d_scratch, 1, 0));
     LCU(cudaMemcpy(out, d_out, out_c * sizeof(float2), cudaMemcpyDeviceToHost));
-    cudaFree(d_tw);
-    cudaFree(d_st);
-    cudaFree(d_in);
-    cudaFree(d_out);
-    cudaFree(d_scratch);
     return SC_OK;
 }
 
