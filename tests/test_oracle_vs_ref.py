@@ -59,3 +59,65 @@ def test_tx_random(oracle, ref):
         for _ in range(8):
             b = rng.integers(0, 2, 62).astype(np.uint8)
             assert np.array_equal(oracle.tx_data(st, b), ref.tx_data(b))
+
+
+def test_f3_fix_removes_the_undefined_behaviour(tmp_path, gold):
+    """the reference's decimated_frame[562] is written up to index 751.  Built under
+    ASan/UBSan, the reference with the one-line fix the oracle build applies is clean on the shipped file,
+    and without it the sanitizer reports the out-of-bounds access (so the fix is necessary and sufficient)."""
+    import os
+    import shutil
+    import subprocess
+    ref = "/root/reference"
+    if not os.path.exists(os.path.join(ref, "src", "qpsk.c")) or shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("needs /root/reference")
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    pre, post = open(os.path.join(here, "ref_harness_pre.h")).read(), open(os.path.join(here, "ref_harness_post.c")).read()
+    src = open(os.path.join(ref, "src", "qpsk.c")).read()
+    drv = tmp_path / "drv.c"
+    drv.write_text('#include <stdio.h>\n#include <stdint.h>\n'
+                   'void ref_run_stream(const int16_t in[], int n_frames, int wide, uint8_t bits[], void *stats);\n'
+                   'int main(int c, char **v){ FILE *f = fopen(v[1], "rb"); static int16_t x[30000]; size_t n = fread(x, 2, 30000, f);'
+                   ' static uint8_t bits[20 * 62]; ref_run_stream(x, (int) (n / 1880), 0, bits, NULL); puts("done"); return 0; }\n')
+    raw = tmp_path / "in.raw"
+    gold("preamble_qpsk_8k.raw").tofile(raw)
+    others = [os.path.join(ref, "src", f + ".c") for f in ("fir", "kalman", "equalizer", "scramble", "constants", "fft")]
+    out = {}
+    for name, body in (("fixed", src.replace("decimated_frame[562]", "decimated_frame[752]")), ("unfixed", src)):
+        c = tmp_path / (name + ".c")
+        c.write_text(pre + body + post)
+        exe = tmp_path / name
+        r = subprocess.run(["gcc", "-std=gnu11", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-w",
+                            "-I", os.path.join(ref, "headers"), str(c), str(drv)] + others + ["-lm", "-o", str(exe)],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            import pytest
+            pytest.skip("sanitizer runtime not available: " + r.stderr[-200:])
+        out[name] = subprocess.run([str(exe), str(raw)], capture_output=True, text=True, timeout=120)
+    assert "done" in out["fixed"].stdout and "runtime error" not in out["fixed"].stderr and "ERROR" not in out["fixed"].stderr
+    assert "out of bounds" in out["unfixed"].stderr
+
+
+def test_oracle_restatement_is_sanitizer_clean(tmp_path, oracle):
+    """The restatement itself under ASan/UBSan on a noisy loop-back stream."""
+    import os
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    drv = tmp_path / "drv.c"
+    drv.write_text('#include <stdio.h>\n#include <stdint.h>\n#include "sc_oracle.h"\n'
+                   'int main(int c, char **v){ FILE *f = fopen(v[1], "rb"); static int16_t x[40000]; size_t n = fread(x, 2, 40000, f);'
+                   ' static uint8_t bits[32 * 62]; static sco_frame_stats st[32]; sco_run_stream(x, (int) (n / 1880), 0, 0.0f, bits, st);'
+                   ' int v2 = 0; for (int i = 0; i < (int) (n / 1880); i++) v2 += st[i].valid; printf("done %d\\n", v2); return 0; }\n')
+    rng = np.random.default_rng(3)
+    x = synth_streams(oracle, rng, 1, 20, noise_levels=(500.0,))[0]
+    raw = tmp_path / "in.raw"
+    x.tofile(raw)
+    exe = tmp_path / "o"
+    r = subprocess.run(["gcc", "-std=gnu11", "-O1", "-g", "-ffp-contract=off", "-fsanitize=address,undefined", "-I", here,
+                        os.path.join(here, "sc_oracle.c"), str(drv), "-lm", "-o", str(exe)], capture_output=True, text=True)
+    if r.returncode != 0:
+        import pytest
+        pytest.skip("sanitizer runtime not available")
+    run = subprocess.run([str(exe), str(raw)], capture_output=True, text=True, timeout=120)
+    assert run.stdout.startswith("done") and "runtime error" not in run.stderr and "ERROR" not in run.stderr
