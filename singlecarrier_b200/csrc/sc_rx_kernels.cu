@@ -140,7 +140,11 @@ __device__ __forceinline__ void fe_fir(const float2 *__restrict__ buf, int front
     }
 }
 
-template <bool WIDE>
+// GENERIC = false: every frame pointer is 4-byte aligned (checked by the launcher), loads are
+// coalesced 32-bit pairs.  GENERIC = true: any alignment, scalar 16-bit loads, same arithmetic.
+// rx_timing is 128..255 whenever the front-end runs, so the first sample
+// needed (rx_timing - 48) is never before the frame; it is clamped to keep a corrupt state in bounds.
+template <bool WIDE, bool GENERIC>
 __global__ void __launch_bounds__(FE_WARPS * 32, 6)
 frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2 *__restrict__ mix_table,
                 const int *__restrict__ timing_cur, const int *__restrict__ timing_next,
@@ -161,7 +165,6 @@ frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2
 
     // warp-uniform set-up
     int base = 0, shift = 0, base2 = 0;
-    bool fast = false;
     const int16_t *frame = in;
     const float2 *tab = mix_table;
     const uint32_t *fp = nullptr;
@@ -170,10 +173,9 @@ frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2
     for (int k = 0; k < FE_KN; k++) raw[k] = 0u;
     if (active) {
         const int T = timing_cur[s];
-        base = min(T, 2 * PRE - 1) - (NTAPS - 1);      // first sample needed; 80..207 once T is 128..255
+        base = max(min(T, 2 * PRE - 1) - (NTAPS - 1), 0);  // first sample needed: 80..207 for T in 128..255
         frame = in + s * stream_stride;
-        fast = base >= 0 && ((((uintptr_t) frame) & 3) == 0);
-        if (fast) {
+        if (!GENERIC) {
             // ---- stage 1: pass A's global loads (coalesced 4-byte loads, the kernel's only HBM reads) ----
             base2 = base & ~1;
             shift = base - base2;
@@ -189,7 +191,7 @@ frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2
         const int h0 = h * CYC * FE_PASS_OUT;
         const int front = FE_FRONT + ((shift + h0) & 1);       // makes every staged pair 16-byte aligned
         if (active) {
-            if (fast) {
+            if (!GENERIC) {
                 if (h == 0) {
                     fe_stage<FE_KA_LO>(mix, raw, tab, lane, front - shift - h0);
                     fe_load<FE_KB_LO>(raw, fp, lane, base2);       // pass B's loads fly during pass A's FIR
@@ -197,17 +199,11 @@ frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2
                     fe_stage<FE_KB_LO>(mix, raw, tab, lane, front - shift - h0);
                 }
             } else {
-                // generic path (odd byte alignment, or the cold-start timing T < 48 where samples
-                // before the frame are silence): same arithmetic, scalar loads
                 for (int rel = lane; rel < FE_PASS_SAMP; rel += 32) {
                     const int t = base + h0 + rel;
-                    float2 v = make_float2(0.f, 0.f);
-                    if (t >= 0) {
-                        const float x = (float) frame[t];
-                        const float2 ph = __ldg(mix_table + t);
-                        v = make_float2(__fmul_rn(ph.x, x), __fmul_rn(ph.y, x));
-                    }
-                    mix[front + rel] = v;
+                    const float x = (float) frame[t];
+                    const float2 ph = __ldg(mix_table + t);
+                    mix[front + rel] = make_float2(__fmul_rn(ph.x, x), __fmul_rn(ph.y, x));
                 }
             }
         }
@@ -332,13 +328,20 @@ cudaError_t launch_frontend(bool wide, const int16_t *in, long stream_stride, co
                             const int *timing_cur, const int *timing_next, float2 *win, int *max_index,
                             float *max_value, int n_streams, cudaStream_t st) {
     const int grid = (n_streams + FE_WARPS - 1) / FE_WARPS;
-    static const int extra_smem = getenv("SC_FE_EXTRA_SMEM") ? atoi(getenv("SC_FE_EXTRA_SMEM")) : 0;   // occupancy experiments
-    if (wide)
-        frontend_kernel<true><<<grid, FE_WARPS * 32, extra_smem, st>>>(in, stream_stride, mix_table, timing_cur, timing_next,
-                                                              win, max_index, max_value, n_streams);
-    else
-        frontend_kernel<false><<<grid, FE_WARPS * 32, extra_smem, st>>>(in, stream_stride, mix_table, timing_cur, timing_next,
-                                                               win, max_index, max_value, n_streams);
+    const int thr = FE_WARPS * 32;
+    // the fast kernel reads the samples as aligned 32-bit pairs: every frame must start on a 4-byte boundary
+    const bool generic = ((((uintptr_t) in) & 3) != 0) || ((stream_stride & 1) != 0);
+#define SC_FE_LAUNCH(W, G)                                                                                      \
+    frontend_kernel<W, G><<<grid, thr, 0, st>>>(in, stream_stride, mix_table, timing_cur, timing_next, win, max_index, \
+                                                max_value, n_streams)
+    if (wide) {
+        if (generic) SC_FE_LAUNCH(true, true);
+        else SC_FE_LAUNCH(true, false);
+    } else {
+        if (generic) SC_FE_LAUNCH(false, true);
+        else SC_FE_LAUNCH(false, false);
+    }
+#undef SC_FE_LAUNCH
     g_launch_count++;
     return cudaGetLastError();
 }

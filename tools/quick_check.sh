@@ -1,4 +1,4 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+python -m pytest tests -x -q -m gpu 2>&1 | tail -1
 python bench.py --no-e2e --no-cpu 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']; o=r['other_kernel']
