@@ -89,8 +89,30 @@ uint64_t sc_launch_count(void);
  * accumulated since the last read (use with SC_OPT_SLAB_PARTS = 1 so launches do not overlap). */
 #define SC_OPT_SLAB_PARTS 1
 #define SC_OPT_PROFILE    2
+/* SC_OPT_H2D_MODE: how sc_rx_frames_host moves the samples to the device (default SC_H2D_COLUMNS; the
+ * environment variable SC_H2D_MODE overrides the default at sc_create).  All modes give identical results. */
+#define SC_OPT_H2D_MODE   3
+#define SC_H2D_COLUMNS    0   /* per frame: one 2-D copy of sample columns 80..1703 (86 % of the bytes)         */
+#define SC_H2D_ROWS       1   /* per block of frames: one 2-D copy, rows trimmed by 256 samples                 */
+#define SC_H2D_FULL       2   /* whole frames: one 2-D copy per block, a plain 1-D copy when streams are dense  */
+#define SC_H2D_COLUMNS_3D 3   /* the COLUMNS bytes as one 3-D copy per block (stream_stride % 1880 == 0)        */
 int  sc_set_option(sc_modem *m, int option, int64_t value);
 int  sc_profile_read(sc_modem *m, double out[4]);
+/* bytes queued host->device (out[0]) and device->host (out[1]) by sc_rx_frames_host since sc_create */
+int  sc_transfer_bytes(const sc_modem *m, uint64_t out[2]);
+/* frees the process-wide device caches (FFT twiddle / permutation tables) */
+int  sc_release_caches(void);
+
+/* ---- checkpoint / resume (the reference cannot even reset its statics, qpsk.c:34-53) --- */
+
+/* Everything a bank needs to continue bit-exactly in another handle or process: per stream rx_timing, the
+ * tracker window, the pending (max_index, max_value) and the last frame of samples; per bank the call
+ * index, RXMemory (src/scramble.c:42), fbb_rx_phase (qpsk.c:50) and the last frame's phasor table.
+ * sc_state_size() bytes are written to / read from HOST memory; import needs a bank created with the same
+ * n_streams, flags and foffset_hz (SC_EINVAL otherwise) and also clears a failed-batch condition. */
+int64_t sc_state_size(const sc_modem *m);
+int  sc_state_export(sc_modem *m, void *buf, int64_t buf_bytes);
+int  sc_state_import(sc_modem *m, const void *buf, int64_t buf_bytes);
 
 /* ---- RX: replaces the while(1) loop of main() calling qpsk_rx_frame(), qpsk.c:436-458 --- */
 
@@ -208,6 +230,51 @@ int sc_lock_stats_dev(int device, const sc_frame_result *results, int64_t n_stre
  * tracking kernel's branch-free reciprocal differs from the correctly rounded one (expected 0 for
  * 2^-120 .. 2^120).  *mismatches: device uint64, accumulated into. */
 int sc_selftest_rcp_dev(int device, uint32_t lo_bits, uint32_t hi_bits, uint64_t *mismatches, void *stream);
+
+#define SC_N_BER_COUNTERS 8
+/* Bit errors against the transmitted bits, on the device (BASELINE.json configs 3-5; the reference's only
+ * counter is preamble_frames_detected, qpsk.c:70,193).  results must hold calls 0..n_frames-1 of a cold
+ * started bank.  A valid call n >= 2 found its preamble at decimated index max_index of the window taken
+ * from frame n-2 with the rx_timing in force after call n-2, i.e. at sample
+ * (n-2)*1880 + 5*max_index + rx_timing - 48 (two 24-sample RRC delays) of the stream; it is "aligned" when
+ * that lies within 10 samples of the start of packet j = round((pos - lead_in[s]) / (1880 + gap)).  Its 62
+ * decided bits are the first data frame of packet j; TX does not scramble (qpsk.c:397) and RX
+ * descrambles, so bits ^ keystream(n) ^ tx_bits is the error pattern.
+ *   tx_bits : device, [n_streams][n_packets][8][62] bytes of 0/1 (sc_tx_*_dev's bits_out)
+ *   group   : device int32[n_streams] or NULL (all streams in group 0), values 0..n_groups-1
+ *   counters: device uint64[n_groups][8], ACCUMULATED into: 0 calls (n >= 2), 1 valid, 2 aligned, 3 bits
+ *             compared (62 per aligned call), 4 bit errors, 5..7 reserved (0).  Plain sums. */
+int sc_ber_stats_dev(int device, const sc_frame_result *results, int64_t n_streams, int64_t result_stride,
+                     int n_frames, const uint8_t *tx_bits, int n_packets, const int32_t *lead_in, int gap_samples,
+                     const int32_t *group, int n_groups, uint64_t *counters, void *stream);
+
+/* ---- multi-GPU reduction of the counters (the path's only collective) ------------------ */
+
+/* ncclAllReduce(sum) of n_counters uint64 in place on `stream`; nccl_comm is a ncclComm_t created by the
+ * caller (ncclCommInitRank / ncclCommInitAll) or by the helpers below.  NCCL is bound at run time from the
+ * libnccl.so.2 already loaded in the process (e.g. PyTorch's), else from the system library. */
+int sc_reduce_stats(uint64_t *counters, int n_counters, void *nccl_comm, void *stream);
+#define SC_NCCL_UNIQUE_ID_BYTES 128
+int sc_comm_unique_id(void *id128);                                 /* ncclGetUniqueId (rank 0; broadcast it) */
+int sc_comm_init_rank(void **comm, int n_ranks, int rank, const void *id128, int device);
+int sc_comm_init_all(void **comms, int n_devices, const int *devices);  /* one process, n GPUs */
+int sc_comm_destroy(void *comm);
+
+/* ---- host memory and the PCIe ceiling -------------------------------------------------------------------- */
+
+/* Page-locked host memory placed on the NUMA node of `device` (thread affinity is narrowed to that node's
+ * CPUs while the pages are first touched).  numa_node (may be NULL) receives the node used, -1 if unknown. */
+int sc_host_alloc(void **ptr, size_t bytes, int device, int *numa_node);
+int sc_host_free(void *ptr);
+/* Page-lock caller-owned memory in place (cudaHostRegister), so sc_rx_frames_host copies asynchronously. */
+int sc_host_register(void *ptr, size_t bytes);
+int sc_host_unregister(void *ptr);
+/* Measures plain copies between pinned host memory and `device` for at least min_seconds (CUDA events):
+ * row_bytes == 0: contiguous cudaMemcpyAsync of buffer_bytes; else cudaMemcpy2DAsync of rows of row_bytes
+ * taken every src_pitch_bytes.  d2h != 0 reverses the direction.  Used by bench.py on all ranks at once to
+ * establish the platform ceiling that sc_rx_frames_host is judged against. */
+int sc_h2d_probe(int device, size_t buffer_bytes, size_t row_bytes, size_t src_pitch_bytes, double min_seconds,
+                 int d2h, double *gbytes_per_s);
 
 /* ---- small utilities used by host code and tests --------------------------------------- */
 

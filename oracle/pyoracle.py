@@ -271,3 +271,39 @@ class Reference:
 
     def global_f32(self, name: str) -> C.c_float:
         return C.c_float.in_dll(self.lib, name)
+
+
+def synth_bench_stream(oracle, seed: int, stream_id: int, n_samples: int) -> np.ndarray:
+    """One stream of bench.py's workload made entirely on the CPU (no GPU, no product code): the reference's
+    packet structure from the oracle's TX (640 preamble + 8 x 155 data + 903 dead air, random lead-in), then the
+    same channel model as the device generator -- rotation of the analytic signal by exp(j(2 pi df t + phi)),
+    df ~ U(-20, 20) Hz, and real AWGN at Eb/N0 = stream_id mod 13 dB -- saturated to int16.  Deterministic in
+    (seed, stream_id); used by ``bench.py --impl reference`` so that arm never loads the CUDA library."""
+    rng = np.random.default_rng([seed & 0x7fffffff, stream_id])
+    st = oracle.new_state()
+    period = FRAME_SIZE + 903
+    lead = int(rng.integers(0, period))
+    parts, n = [np.zeros(lead, np.int16)], lead
+    while n < n_samples:
+        parts.append(oracle.tx_preamble(st))
+        for _ in range(8):
+            parts.append(oracle.tx_data(st, rng.integers(0, 2, 62).astype(np.uint8)))
+        parts.append(np.zeros(903, np.int16))
+        n += period
+    x = np.concatenate(parts)[:n_samples].astype(np.float64)
+    # analytic signal by the FFT (Hilbert) method, then the frequency / phase offset
+    spec = np.fft.fft(x)
+    h = np.zeros(n_samples)
+    h[0] = 1.0
+    h[1:(n_samples + 1) // 2] = 2.0
+    if n_samples % 2 == 0:
+        h[n_samples // 2] = 1.0
+    xa = np.fft.ifft(spec * h)
+    df, phi = rng.uniform(-20.0, 20.0), rng.uniform(0.0, 2 * np.pi)
+    t = np.arange(n_samples) / 8000.0
+    y = (xa * np.exp(1j * (2 * np.pi * df * t + phi))).real
+    ebn0_db = float(stream_id % 13)
+    p_sig = (16384.0 * 0.48) ** 2
+    sigma = np.sqrt(p_sig * 8000.0 / (2.0 * 1600.0 * 2.0 * 10.0 ** (ebn0_db / 10.0)))
+    y = y + rng.normal(0.0, sigma, n_samples)
+    return np.clip(np.rint(y), -32767, 32767).astype(np.int16)

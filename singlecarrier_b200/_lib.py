@@ -66,6 +66,22 @@ def _load() -> C.CDLL:
     sig("sc_fftri_batch_dev", i32, i32, i64, i32, vp, vp, vp)
     sig("sc_lock_stats_dev", i32, i32, vp, i64, i64, i32, vp, vp)
     sig("sc_selftest_rcp_dev", i32, i32, u32, u32, vp, vp)
+    sig("sc_transfer_bytes", i32, vp, C.POINTER(C.c_uint64))
+    sig("sc_release_caches", i32)
+    sig("sc_state_size", i64, vp)
+    sig("sc_state_export", i32, vp, vp, i64)
+    sig("sc_state_import", i32, vp, vp, i64)
+    sig("sc_ber_stats_dev", i32, i32, vp, i64, i64, i32, vp, i32, vp, i32, vp, i32, vp, vp)
+    sig("sc_reduce_stats", i32, vp, i32, vp, vp)
+    sig("sc_comm_unique_id", i32, vp)
+    sig("sc_comm_init_rank", i32, C.POINTER(vp), i32, i32, vp, i32)
+    sig("sc_comm_init_all", i32, C.POINTER(vp), i32, C.POINTER(i32))
+    sig("sc_comm_destroy", i32, vp)
+    sig("sc_host_alloc", i32, C.POINTER(vp), C.c_size_t, i32, C.POINTER(i32))
+    sig("sc_host_free", i32, vp)
+    sig("sc_host_register", i32, vp, C.c_size_t)
+    sig("sc_host_unregister", i32, vp)
+    sig("sc_h2d_probe", i32, i32, C.c_size_t, C.c_size_t, C.c_size_t, C.c_double, i32, C.POINTER(C.c_double))
     sig("sc_nco_table_host", i32, vp, i32, u32, i32, vp)
     sig("sc_keystream_word", u64, u32)
     return lib

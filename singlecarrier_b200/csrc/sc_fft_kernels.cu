@@ -84,9 +84,9 @@ __device__ __forceinline__ void bfly5(c32 *F, const c32 *tw, int base, int u, in
 
 // mode 0: complex transform; 1: encode_fftr (real in -> n/2+1 complex out); 2: encode_fftri
 __global__ void __launch_bounds__(256)
-fft_kernel(FftPlan plan, const c32 *__restrict__ tw, const c32 *__restrict__ super_tw, int mode,
-           const void *__restrict__ in, void *__restrict__ out, c32 *__restrict__ scratch, int use_smem,
-           long n_batches) {
+fft_kernel(FftPlan plan, const c32 *__restrict__ tw, const c32 *__restrict__ super_tw,
+           const int *__restrict__ perm, int mode, const void *__restrict__ in, void *__restrict__ out,
+           c32 *__restrict__ scratch, int use_smem, long n_batches) {
     extern __shared__ __align__(16) unsigned char fft_smem[];
     const int n = plan.n;                                  // complex length of the core transform
     c32 *F, *G;
@@ -116,17 +116,8 @@ fft_kernel(FftPlan plan, const c32 *__restrict__ tw, const c32 *__restrict__ sup
             for (int i = t; i < n; i += nt) G[i] = x[i];
         }
         __syncthreads();
-        // ---- leaves of kf_work (src/fft.c:399-404): digit-reversed gather
-        for (int i = t; i < n; i += nt) {
-            int rem = i, src = 0, mult = 1;
-            for (int l = 0; l < plan.n_stages; l++) {
-                const int q = rem / plan.m[l];
-                rem -= q * plan.m[l];
-                src += q * mult;
-                mult *= plan.p[l];
-            }
-            F[i] = G[src];
-        }
+        // ---- leaves of kf_work (src/fft.c:399-404): digit-reversed gather through the host-made table
+        for (int i = t; i < n; i += nt) F[i] = G[__ldg(perm + i)];
         __syncthreads();
         // ---- butterflies, innermost factor first (the recursion unwinds this way, src/fft.c:412-430)
         int fs = n;
@@ -182,20 +173,154 @@ fft_kernel(FftPlan plan, const c32 *__restrict__ tw, const c32 *__restrict__ sup
     }
 }
 
-cudaError_t launch_fft(const FftPlan &plan, const float2 *tw, const float2 *super_tw, int mode, const void *in,
-                       void *out, float2 *scratch, long n_batches, cudaStream_t st) {
+// ------------------------------------------------------------------------------------------------
+// n = 256 = 4 x 4 x 4 x 4 (the size a 128-lag x 128-tap correlation needs): one WARP per
+// transform, 8 points per lane in registers, no shared memory.  kf_factor gives (4,64)(4,16)(4,4)(4,1), so
+// working-array index i = 64 d0 + 16 d1 + 4 d2 + d3 holds input element d0 + 4 d1 + 16 d2 + 64 d3 and the
+// stages run over d3, d2, d1, d0 in that order (the recursion unwinds innermost first).  A radix-4 butterfly
+// needs its digit in the register index; between stages one or two index bits are exchanged between lane
+// and register position with __shfl_xor_sync (5 exchanges of 4 complex values per lane in all):
+//
+//   position     L0    L1    L2    L3    L4  | R0    R1    R2        (L = lane bit, R = register-index bit)
+//   load         d0lo  d0hi  d1lo  d1hi  d2lo| d2hi  d3lo  d3hi      coalesced: element t + 32 r
+//   stage d3                                                         legs r = b + 2k          (b = R0)
+//   L4<->R2      d0lo  d0hi  d1lo  d1hi  d3hi| d2hi  d3lo  d2lo
+//   stage d2                                                         legs r = (k>>1) + 2b + 4(k&1)   (b = R1)
+//   L2<->R2, L3<->R0
+//                d0lo  d0hi  d2lo  d2hi  d3hi| d1hi  d3lo  d1lo
+//   stage d1                                                         same leg mapping
+//   L0<->R2, L1<->R1
+//                d1lo  d3lo  d2lo  d2hi  d3hi| d1hi  d0hi  d0lo
+//   stage d0                                                         legs r = b + 2(k>>1) + 4(k&1)   (b = R0)
+//   store        i = 64 d0 + 16 d1 + 4 d2 + d3: for a fixed register the 32 lanes cover 32 consecutive
+//                outputs (in permuted lane order), so every store instruction writes one 256-byte segment.
+//
+// Every butterfly is kf_bfly4's expression sequence (src/fft.c:218-266) including the multiplications by
+// twiddle 0, with the host-made twiddle table, so the output is bit-identical to src/fft.c.
+// ------------------------------------------------------------------------------------------------
+template <bool INVERSE>
+__device__ __forceinline__ void bfly4_reg(c32 &a0, c32 &a1, c32 &a2, c32 &a3, c32 t1, c32 t2, c32 t3) {
+    const c32 s0 = cmul(a1, t1), s1 = cmul(a2, t2), s2 = cmul(a3, t3);
+    const c32 s5 = csub(a0, s1);
+    const c32 f0 = cadd(a0, s1);
+    const c32 s3 = cadd(s0, s2), s4 = csub(s0, s2);
+    a2 = csub(f0, s3);
+    a0 = cadd(f0, s3);
+    if (INVERSE) {
+        a1 = mk(__fsub_rn(s5.r, s4.i), __fadd_rn(s5.i, s4.r));
+        a3 = mk(__fadd_rn(s5.r, s4.i), __fsub_rn(s5.i, s4.r));
+    } else {
+        a1 = mk(__fadd_rn(s5.r, s4.i), __fsub_rn(s5.i, s4.r));
+        a3 = mk(__fsub_rn(s5.r, s4.i), __fadd_rn(s5.i, s4.r));
+    }
+}
+
+// exchange lane bit LANE_MASK with register-index bit REG_BIT of an 8-value-per-lane array
+template <int LANE_MASK, int REG_BIT>
+__device__ __forceinline__ void xchg_bit(c32 (&v)[8], int lane) {
+    const bool up = (lane & LANE_MASK) != 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        if (r & (1 << REG_BIT)) continue;
+        const int r1 = r | (1 << REG_BIT);
+        const float sr = up ? v[r].r : v[r1].r, si = up ? v[r].i : v[r1].i;
+        const float gr = __shfl_xor_sync(0xffffffffu, sr, LANE_MASK), gi = __shfl_xor_sync(0xffffffffu, si, LANE_MASK);
+        if (up) v[r] = mk(gr, gi);
+        else v[r1] = mk(gr, gi);
+    }
+}
+
+constexpr int FFT256_WARPS = 4;
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(FFT256_WARPS * 32)
+fft256_warp_kernel(const c32 *__restrict__ tw, const float2 *__restrict__ in, float2 *__restrict__ out, long n_batches) {
+    const int lane = threadIdx.x & 31;
+    const long warp = (long) blockIdx.x * FFT256_WARPS + (threadIdx.x >> 5);
+    const long n_warps = (long) gridDim.x * FFT256_WARPS;
+    const int L0 = lane & 1, L1 = (lane >> 1) & 1, L2 = (lane >> 2) & 1, L3 = (lane >> 3) & 1, L4 = (lane >> 4) & 1;
+
+    // twiddles of this lane (they depend on the lane only, so they are fetched once per warp):
+    // stage d2: u = d3 = R1 + 2 L4, tw[16 u k]; stage d1: u = 4 d2 + d3 = 4(L2 + 2 L3) + R1 + 2 L4, tw[4 u k];
+    // stage d0: u = 16 d1 + 4 d2 + d3 = 16(L0 + 2 R0) + 4(L2 + 2 L3) + L1 + 2 L4, tw[u k]
+    const c32 tw0 = tw[0];
+    c32 t2[2][3], t1[2][3], t0[2][3];
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+        const int u2 = b + 2 * L4, u1 = 4 * (L2 + 2 * L3) + b + 2 * L4, u0 = 16 * (L0 + 2 * b) + 4 * (L2 + 2 * L3) + L1 + 2 * L4;
+#pragma unroll
+        for (int k = 1; k < 4; k++) {
+            t2[b][k - 1] = tw[16 * u2 * k];
+            t1[b][k - 1] = tw[4 * u1 * k];
+            t0[b][k - 1] = tw[u0 * k];
+        }
+    }
+
+    c32 v[8], nx[8];
+    if (warp < n_batches) {
+        const float2 *x = in + warp * 256 + lane;
+#pragma unroll
+        for (int r = 0; r < 8; r++) nx[r] = from2(__ldg(x + 32 * r));
+    }
+    for (long b = warp; b < n_batches; b += n_warps) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[r] = nx[r];
+        if (b + n_warps < n_batches) {                       // next transform's loads fly during this one's math
+            const float2 *x = in + (b + n_warps) * 256 + lane;
+#pragma unroll
+            for (int r = 0; r < 8; r++) nx[r] = from2(__ldg(x + 32 * r));
+        }
+        // stage d3 (m = 1, every twiddle is tw[0])
+#pragma unroll
+        for (int q = 0; q < 2; q++) bfly4_reg<INVERSE>(v[q], v[q + 2], v[q + 4], v[q + 6], tw0, tw0, tw0);
+        xchg_bit<16, 2>(v, lane);
+        // stage d2 (m = 4)
+#pragma unroll
+        for (int q = 0; q < 2; q++) bfly4_reg<INVERSE>(v[2 * q], v[2 * q + 4], v[2 * q + 1], v[2 * q + 5], t2[q][0], t2[q][1], t2[q][2]);
+        xchg_bit<4, 2>(v, lane);
+        xchg_bit<8, 0>(v, lane);
+        // stage d1 (m = 16)
+#pragma unroll
+        for (int q = 0; q < 2; q++) bfly4_reg<INVERSE>(v[2 * q], v[2 * q + 4], v[2 * q + 1], v[2 * q + 5], t1[q][0], t1[q][1], t1[q][2]);
+        xchg_bit<1, 2>(v, lane);
+        xchg_bit<2, 1>(v, lane);
+        // stage d0 (m = 64)
+#pragma unroll
+        for (int q = 0; q < 2; q++) bfly4_reg<INVERSE>(v[q], v[q + 4], v[q + 2], v[q + 6], t0[q][0], t0[q][1], t0[q][2]);
+        // i = 64 (R2 + 2 R1) + 16 (L0 + 2 R0) + 4 (L2 + 2 L3) + L1 + 2 L4
+        float2 *y = out + b * 256 + 16 * L0 + L1 + 4 * L2 + 8 * L3 + 2 * L4;
+#pragma unroll
+        for (int r = 0; r < 8; r++) y[64 * ((r >> 2) + 2 * ((r >> 1) & 1)) + 32 * (r & 1)] = to2(v[r]);
+    }
+}
+
+cudaError_t launch_fft(const FftPlan &plan, const float2 *tw, const float2 *super_tw, const int *perm, int mode,
+                       const void *in, void *out, float2 *scratch, long n_batches, cudaStream_t st) {
     const int n = plan.n;
+    const bool radix4x4 = plan.n_stages == 4 && plan.p[0] == 4 && plan.p[1] == 4 && plan.p[2] == 4 && plan.p[3] == 4;
+    if (mode == 0 && n == 256 && radix4x4 && in != out) {                  // 4 x 4 x 4 x 4: register/warp-shuffle specialisation
+        const long want = (n_batches + FFT256_WARPS - 1) / FFT256_WARPS;
+        const int grid = (int) std::min<long>(want, 148L * 12);
+        if (plan.inverse)
+            fft256_warp_kernel<true><<<grid, FFT256_WARPS * 32, 0, st>>>(reinterpret_cast<const c32 *>(tw), (const float2 *) in,
+                                                                          (float2 *) out, n_batches);
+        else
+            fft256_warp_kernel<false><<<grid, FFT256_WARPS * 32, 0, st>>>(reinterpret_cast<const c32 *>(tw), (const float2 *) in,
+                                                                           (float2 *) out, n_batches);
+        g_launch_count++;
+        return cudaGetLastError();
+    }
     const size_t smem = (size_t) 2 * n * sizeof(float2);
-    const int use_smem = smem <= 64 * 1024;
+    const int use_smem = !fft_needs_scratch(n);
     int grid = (int) std::min<long>(n_batches, 148L * 4);
     if (!use_smem) grid = (int) std::min<long>(grid, FFT_SCRATCH_CTAS);
     if (use_smem && smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FFT_SMEM_LIMIT);
         if (e != cudaSuccess) return e;
     }
     const int threads = n >= 1024 ? 256 : (n >= 256 ? 128 : 64);
     fft_kernel<<<grid, threads, use_smem ? smem : 0, st>>>(plan, reinterpret_cast<const c32 *>(tw),
-                                                           reinterpret_cast<const c32 *>(super_tw), mode, in, out,
+                                                           reinterpret_cast<const c32 *>(super_tw), perm, mode, in, out,
                                                            reinterpret_cast<c32 *>(scratch), use_smem, n_batches);
     g_launch_count++;
     return cudaGetLastError();

@@ -13,15 +13,17 @@ namespace sc {
 extern std::atomic<unsigned long long> g_launch_count;
 
 // sc_rx_kernels.cu
-cudaError_t launch_nco_table(float2 *phase_state, float2 rect, const int *seg_len, int n_seg, float scale,
+enum { NCO_RX = 0, NCO_TX_PACKET = 1, NCO_SINGLE = 2 };      // run lengths between phasor renormalisations
+cudaError_t launch_nco_table(float2 *phase_state, float2 rect, int pattern, int seg_single, int n_seg, float scale,
                              float2 *out, cudaStream_t st);
 cudaError_t launch_frontend(bool wide, const int16_t *in, long stream_stride, const float2 *mix_table,
                             const int *timing_cur, const int *timing_next, float2 *win, int *max_index,
                             float *max_value, int n_streams, cudaStream_t st);
 cudaError_t launch_track(bool debug_eq, const float2 *win, const int *max_index, const float *max_value,
                          const int *timing_cur, int *timing_next, sc_frame_result *results, long result_stride,
-                         float *eq_dbg, uint32_t call_index, unsigned long long keystream, int n_streams,
-                         cudaStream_t st);
+                         float *eq_dbg, float *state_dbg, uint32_t call_index, unsigned long long keystream,
+                         int n_streams, cudaStream_t st);
+constexpr int TRACK_STATE_FLOATS = 48;   // C[5], G[5], U[10] complex, D[5], KY, 2 pad: the drop-in shim's view
 
 // sc_stage_kernels.cu
 cudaError_t launch_fir_batch(bool wide, long n_streams, float2 *memory, float2 *sample, long sample_stride,
@@ -39,14 +41,24 @@ struct FftPlan {
     int p[32], m[32];   // kf_factor(): radix and remaining length per stage (src/fft.c:433-459)
 };
 constexpr int FFT_SCRATCH_CTAS = 64;
-cudaError_t launch_fft(const FftPlan &plan, const float2 *tw, const float2 *super_tw, int mode, const void *in,
-                       void *out, float2 *scratch, long n_batches, cudaStream_t st);
+constexpr int FFT_SMEM_LIMIT = 64 * 1024;
+inline bool fft_needs_scratch(int n) { return (size_t) 2 * n * sizeof(float2) > (size_t) FFT_SMEM_LIMIT; }
+void fft_make_plan(int n, int inverse, FftPlan *plan);
+void fft_make_permutation(const FftPlan &plan, int *perm);
+void fft_make_twiddles(int n, int inverse, float2 *tw);
+void fft_make_super_twiddles(int ncfft, int inverse, float2 *tw);
+cudaError_t launch_fft(const FftPlan &plan, const float2 *tw, const float2 *super_tw, const int *perm, int mode,
+                       const void *in, void *out, float2 *scratch, long n_batches, cudaStream_t st);
 
 cudaError_t launch_selftest_rcp(unsigned lo, unsigned hi, unsigned long long *mismatches, cudaStream_t st);
 
 // sc_stats_kernels.cu
 cudaError_t launch_lock_stats(const sc_frame_result *results, long n_streams, long result_stride, int n_frames,
                               unsigned long long *counters, cudaStream_t st);
+
+cudaError_t launch_ber_stats(const sc_frame_result *results, long n_streams, long result_stride, int n_frames,
+                             const uint8_t *tx_bits, int n_packets, const int *lead_in, int gap, const int *group,
+                             int n_groups, unsigned long long *counters, cudaStream_t st);
 
 // sc_tx_kernels.cu
 struct TxArgs {

@@ -92,7 +92,7 @@ void qpsk_demod(uint8_t bits[], complex float symbol) {
 }
 
 int qpsk_rx_frame(int16_t in[], uint8_t bits[]) {
-    int valid = scl_rx_frame(in, bits, (float *) eq_coeff);
+    int valid = scl_rx_frame(in, bits, (float *) eq_coeff, (float *) kalman_gain, &kalman_y);
     if (valid < 0) must(valid, "qpsk_rx_frame");
     preamble_frames_detected++;
     return valid;

@@ -18,9 +18,9 @@
 
 namespace sc {
 int api_fail(int code, const char *msg);
-void fft_make_plan(int n, int inverse, FftPlan *plan);
-void fft_make_twiddles(int n, int inverse, float2 *tw);
-void fft_make_super_twiddles(int ncfft, int inverse, float2 *tw);
+uint16_t modem_lfsr_rx(const sc_modem *m);
+void modem_set_lfsr_rx(sc_modem *m, uint16_t v);
+void modem_set_state_dbg(sc_modem *m, float *p);
 
 // the reference's process-global equalizer / scrambler state (src/kalman.c:19-35, src/scramble.c:41-42)
 struct LegacyState {
@@ -126,8 +126,8 @@ struct Legacy {
     int device = 0;
     LegacyState *d_state = nullptr;
     sc_modem *bank = nullptr;
+    float *d_track_state = nullptr;          // the bank's tracker state after its last call (48 floats)
     float2 *d_txfilter = nullptr, *d_txphase = nullptr;
-    int *d_seg = nullptr;
     float2 tx_rect;
     std::mutex mu;
 } g;
@@ -174,7 +174,6 @@ int ensure() {
     LCU(cudaMalloc(&g.d_txphase, sizeof(float2)));
     const float2 one = make_float2(1.0f, 0.0f);      // fbb_tx_phase = cmplx(0.0f), qpsk.c:375
     LCU(cudaMemcpy(g.d_txphase, &one, sizeof one, cudaMemcpyHostToDevice));
-    LCU(cudaMalloc(&g.d_seg, sizeof(int)));
     const double tau = 2.0f * M_PI;
     const float xr = (float) (tau * 1100.0f / 8000.0f);                       // cmplx(TAU * CENTER / FS), qpsk.c:376
     g.tx_rect = make_float2(cosf(xr), sinf(xr));
@@ -263,7 +262,11 @@ extern "C" int scl_misc(int op, float a, float b, float *out) {
     return SC_OK;
 }
 
-extern "C" int scl_rx_frame(const int16_t *in, uint8_t *bits, float *eq_coeff) {
+// qpsk_rx_frame(), src/qpsk.c:133-239, on a one-stream bank.  The reference's globals stay coherent with it:
+// the descrambler register RXMemory is the one scramble(&x, rx) / scramble_init(rx) / data_eq() use
+// (src/scramble.c:42, src/equalizer.c:87), and eq_coeff, kalman_gain, kalman_y and the internal u / d are left
+// as the frame's last data_eq() left them (src/kalman.c:19-35), so a caller may continue with train_eq().
+extern "C" int scl_rx_frame(const int16_t *in, uint8_t *bits, float *eq_coeff, float *gain, float *ky) {
     std::lock_guard<std::mutex> lock(g.mu);
     int rc = ensure();
     if (rc != SC_OK) return rc;
@@ -271,12 +274,28 @@ extern "C" int scl_rx_frame(const int16_t *in, uint8_t *bits, float *eq_coeff) {
         // firwide = false, FOFFSET = 0 as compiled into the reference (qpsk.c:60,67)
         rc = sc_create(&g.bank, g.device, 1, SC_FLAG_DEBUG_EQ, 0.0f);
         if (rc != SC_OK) return rc;
+        LCU(cudaMalloc(&g.d_track_state, TRACK_STATE_FLOATS * sizeof(float)));
+        modem_set_state_dbg(g.bank, g.d_track_state);
     }
+    LegacyState h;
+    LCU(cudaMemcpy(&h, g.d_state, sizeof h, cudaMemcpyDeviceToHost));
+    modem_set_lfsr_rx(g.bank, (uint16_t) h.lfsr_rx);
     sc_frame_result r;
     float eq[10];
     rc = sc_rx_frames_host(g.bank, in, SC_FRAME_SIZE, 1, &r, 1, eq);
     if (rc != SC_OK) return rc;
-    memcpy(eq_coeff, eq, sizeof eq);
+    float ts[TRACK_STATE_FLOATS];
+    LCU(cudaMemcpy(ts, g.d_track_state, sizeof ts, cudaMemcpyDeviceToHost));
+    memcpy(h.C, ts, sizeof h.C);
+    memcpy(h.G, ts + 10, sizeof h.G);
+    memcpy(h.U, ts + 20, sizeof h.U);
+    memcpy(h.D, ts + 40, sizeof h.D);
+    h.KY = ts[45];
+    h.lfsr_rx = modem_lfsr_rx(g.bank);
+    LCU(cudaMemcpy(g.d_state, &h, sizeof h, cudaMemcpyHostToDevice));
+    memcpy(eq_coeff, h.C, sizeof h.C);
+    memcpy(gain, h.G, sizeof h.G);
+    *ky = h.KY;
     if (r.valid) sc_unpack_bits(&r, 1, bits);
     return r.valid ? 1 : 0;
 }
@@ -293,11 +312,10 @@ extern "C" int scl_tx_frame(int16_t *samples, const float *symbols, int length, 
     LCU(d_ph.alloc((size_t) n));
     LCU(d_out.alloc((size_t) n));
     LCU(cudaMemcpy(d_sym, symbols, (size_t) length * sizeof(float2), cudaMemcpyHostToDevice));
-    LCU(cudaMemcpy(g.d_seg, &n, sizeof n, cudaMemcpyHostToDevice));
     legacy_tx_stuff_kernel<<<(n + 255) / 256, 256>>>(d_sym, length, d_sig);
     g_launch_count++;
     LCU(launch_fir_batch(false, 1, g.d_txfilter, d_sig, n, n, 0));             // fir(tx_filter, firwide, ...), qpsk.c:296
-    LCU(launch_nco_table(g.d_txphase, g.tx_rect, g.d_seg, 1, 1.0f, d_ph, 0)); // phasor recurrence + renorm, :301-306
+    LCU(launch_nco_table(g.d_txphase, g.tx_rect, NCO_SINGLE, n, 1, 1.0f, d_ph, 0));   // phasor recurrence + renorm, :301-306
     legacy_tx_mix_kernel<<<(n + 255) / 256, 256>>>(d_sig, d_ph, n, preamble ? 8192.0f : 16384.0f, d_out);
     g_launch_count++;
     LCU(cudaGetLastError());
@@ -333,6 +351,11 @@ static int fft_host(int n, int inverse, int mode, const int *factors, const floa
     if ((rc = plan_from_factors(n, inverse, factors, &plan)) != SC_OK) return rc;
     const size_t in_c = mode == 2 ? (size_t) n + 1 : (size_t) n, out_c = mode == 1 ? (size_t) n + 1 : (size_t) n;
     DevBuf<float2> d_tw, d_st, d_in, d_out, d_scratch;
+    DevBuf<int> d_perm;
+    std::vector<int> perm((size_t) n);
+    fft_make_permutation(plan, perm.data());
+    LCU(d_perm.alloc((size_t) n));
+    LCU(cudaMemcpy(d_perm, perm.data(), (size_t) n * sizeof(int), cudaMemcpyHostToDevice));
     LCU(d_tw.alloc((size_t) n));
     LCU(d_in.alloc(in_c));
     LCU(d_out.alloc(out_c));
@@ -342,8 +365,8 @@ static int fft_host(int n, int inverse, int mode, const int *factors, const floa
         LCU(d_st.alloc((size_t) std::max(n / 2, 1)));
         LCU(cudaMemcpy(d_st, super_tw, (size_t) (n / 2) * sizeof(float2), cudaMemcpyHostToDevice));
     }
-    if ((size_t) 2 * n * sizeof(float2) > 64 * 1024) LCU(d_scratch.alloc((size_t) 2 * n));
-    LCU(launch_fft(plan, d_tw, d_st, mode, d_in, d_out, d_scratch, 1, 0));
+    if (fft_needs_scratch(n)) LCU(d_scratch.alloc((size_t) 2 * n));
+    LCU(launch_fft(plan, d_tw, d_st, d_perm, mode, d_in, d_out, d_scratch, 1, 0));
     LCU(cudaMemcpy(out, d_out, out_c * sizeof(float2), cudaMemcpyDeviceToHost));
     return SC_OK;
 }

@@ -13,7 +13,7 @@ int scl_scramble_init(int sr);
 int scl_scramble(uint8_t *v, int sr);
 /* op 0: cnormf(a + bi) -> out[0]; 1: qpsk_mod(bitI=a, bitQ=b) -> out[0..1]; 2: qpsk_demod(a + bi) -> out[0]=Q bit, out[1]=I bit */
 int scl_misc(int op, float a, float b, float *out);
-int scl_rx_frame(const int16_t *in, uint8_t *bits, float *eq_coeff);
+int scl_rx_frame(const int16_t *in, uint8_t *bits, float *eq_coeff, float *gain, float *ky);
 int scl_tx_frame(int16_t *samples, const float *symbols, int length, int preamble);
 int scl_fft(int nfft, int inverse, const int *factors, const float *twiddles, const float *in, float *out);
 int scl_fftr(int ncfft, int inverse, int mode, const int *factors, const float *twiddles, const float *super_twiddles,

@@ -24,18 +24,21 @@ namespace sc {
 // NCO phasor table.  The reference advances one complex phasor per sample by a float recurrence
 // and renormalises it after every frame (qpsk.c:138-147 RX, :301-306 TX).  The sequence does not
 // depend on the data, so it is generated once per batch by a single thread running the identical
-// recurrence and shared by every stream.  seg_len[] lists the run lengths between renormalisations
+// recurrence and shared by every stream.  `pattern` gives the run lengths between renormalisations
 // (RX: 1880 per call; TX: 640,155 x 8 per packet).  scale multiplies the stored value (a power of
 // two, exact): the RX table is stored pre-multiplied by 1/16384 so the mixer is phasor*(float)in.
 // ------------------------------------------------------------------------------------------------
-__global__ void nco_table_kernel(float2 *__restrict__ phase_state, float2 rect, const int *__restrict__ seg_len,
+__global__ void nco_table_kernel(float2 *__restrict__ phase_state, float2 rect, int pattern, int seg_single,
                                  int n_seg, float scale, float2 *__restrict__ out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     c32 ph = from2(*phase_state);
     const c32 r = from2(rect);
     long k = 0;
     for (int s = 0; s < n_seg; s++) {
-        const int len = seg_len[s];
+        // NCO_RX: one run per qpsk_rx_frame() call; NCO_TX_PACKET: 640, then 8 x 155 (qpsk.c:380-405);
+        // NCO_SINGLE: the caller's run length (one qpsk_tx_frame() call of the drop-in shim)
+        const int len = pattern == NCO_RX ? FRAME
+                        : pattern == NCO_TX_PACKET ? ((s % 9) == 0 ? PRE * CYC : NDATA * CYC) : seg_single;
         for (int i = 0; i < len; i++, k++) {
             ph = cmul(ph, r);
             out[k] = make_float2(__fmul_rn(ph.r, scale), __fmul_rn(ph.i, scale));
@@ -287,8 +290,8 @@ template <bool DEBUG_EQ>
 __global__ void __launch_bounds__(TK_THREADS)
 track_kernel(const float2 *__restrict__ win, const int *__restrict__ max_index, const float *__restrict__ max_value,
              const int *__restrict__ timing_cur, int *__restrict__ timing_next, sc_frame_result *__restrict__ results,
-             long result_stride, float *__restrict__ eq_dbg, uint32_t call_index, unsigned long long keystream,
-             int n_streams) {
+             long result_stride, float *__restrict__ eq_dbg, float *__restrict__ state_dbg, uint32_t call_index,
+             unsigned long long keystream, int n_streams) {
     const long s = (long) blockIdx.x * TK_THREADS + threadIdx.x;
     if (s >= n_streams) return;
 
@@ -311,15 +314,34 @@ track_kernel(const float2 *__restrict__ win, const int *__restrict__ max_index, 
             e[2 * i + 1] = o.tk.C[i].i;
         }
     }
+    // the whole equalizer / Kalman state the reference leaves in its globals after the call
+    // (src/kalman.c:19-35): eq_coeff, kalman_gain, u (upper triangle), d, kalman_y -- drop-in shim only
+    if (DEBUG_EQ && state_dbg != nullptr) {
+        float *e = state_dbg + s * TRACK_STATE_FLOATS;
+#pragma unroll
+        for (int i = 0; i < EQ; i++) {
+            e[2 * i] = o.tk.C[i].r;
+            e[2 * i + 1] = o.tk.C[i].i;
+            e[10 + 2 * i] = o.tk.G[i].r;
+            e[10 + 2 * i + 1] = o.tk.G[i].i;
+            e[40 + i] = o.tk.D[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            e[20 + 2 * i] = o.tk.U[i].r;
+            e[20 + 2 * i + 1] = o.tk.U[i].i;
+        }
+        e[45] = o.tk.KY;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host-side launchers (called from sc_api.cu)
 // ------------------------------------------------------------------------------------------------
 
-cudaError_t launch_nco_table(float2 *phase_state, float2 rect, const int *seg_len, int n_seg, float scale,
+cudaError_t launch_nco_table(float2 *phase_state, float2 rect, int pattern, int seg_single, int n_seg, float scale,
                              float2 *out, cudaStream_t st) {
-    nco_table_kernel<<<1, 32, 0, st>>>(phase_state, rect, seg_len, n_seg, scale, out);
+    nco_table_kernel<<<1, 32, 0, st>>>(phase_state, rect, pattern, seg_single, n_seg, scale, out);
     g_launch_count++;
     return cudaGetLastError();
 }
@@ -348,15 +370,15 @@ cudaError_t launch_frontend(bool wide, const int16_t *in, long stream_stride, co
 
 cudaError_t launch_track(bool debug_eq, const float2 *win, const int *max_index, const float *max_value,
                          const int *timing_cur, int *timing_next, sc_frame_result *results, long result_stride,
-                         float *eq_dbg, uint32_t call_index, unsigned long long keystream, int n_streams,
-                         cudaStream_t st) {
+                         float *eq_dbg, float *state_dbg, uint32_t call_index, unsigned long long keystream,
+                         int n_streams, cudaStream_t st) {
     const int grid = (n_streams + TK_THREADS - 1) / TK_THREADS;
     if (debug_eq)
         track_kernel<true><<<grid, TK_THREADS, 0, st>>>(win, max_index, max_value, timing_cur, timing_next, results,
-                                                        result_stride, eq_dbg, call_index, keystream, n_streams);
+                                                        result_stride, eq_dbg, state_dbg, call_index, keystream, n_streams);
     else
         track_kernel<false><<<grid, TK_THREADS, 0, st>>>(win, max_index, max_value, timing_cur, timing_next, results,
-                                                         result_stride, eq_dbg, call_index, keystream, n_streams);
+                                                         result_stride, eq_dbg, state_dbg, call_index, keystream, n_streams);
     g_launch_count++;
     return cudaGetLastError();
 }

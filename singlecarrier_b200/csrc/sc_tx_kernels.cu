@@ -15,24 +15,29 @@
 #include "sc_kernels.h"
 
 #include <algorithm>
+#include <mutex>
 
 namespace sc {
 
 __constant__ float c_taps[2][NTAPS];
 __constant__ uint32_t c_tx_pre_neg[4] = {pre_neg_word(0), pre_neg_word(1), pre_neg_word(2), pre_neg_word(3)};
 
+// the tap table is uploaded once per device; banks may be created from several threads at once
+static std::mutex g_taps_mu;
 static bool g_taps_uploaded[64] = {};
 
 static cudaError_t upload_taps() {
     int dev = 0;
-    cudaGetDevice(&dev);
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(g_taps_mu);
     if (dev >= 0 && dev < 64 && g_taps_uploaded[dev]) return cudaSuccess;
     float h[2][NTAPS];
     for (int k = 0; k < NTAPS; k++) {
         h[0][k] = tap35(k);
         h[1][k] = tap50(k);
     }
-    cudaError_t e = cudaMemcpyToSymbol(c_taps, h, sizeof h);
+    e = cudaMemcpyToSymbol(c_taps, h, sizeof h);
     if (e == cudaSuccess && dev >= 0 && dev < 64) g_taps_uploaded[dev] = true;
     return e;
 }

@@ -136,3 +136,17 @@ def ber_and_lock(res, n_frames: int, wl: Workload, group=None, n_groups: int = 1
         out["bits"][gi] = 62 * out["aligned"][gi]
         out["errors"][gi] = int((errs * (m & ok)).sum())
     return out
+
+
+def ber_and_lock_dev(bank: ModemBank, res, n_frames: int, wl: Workload, group=None, n_groups: int = 1, comm=None):
+    """The same statistics as ber_and_lock(), computed by one kernel (sc_ber_stats_dev) and, when ``comm`` (an
+    NcclComm) is given, summed over all ranks with sc_reduce_stats -- the form a multi-GPU caller uses."""
+    import torch
+    cnt = torch.zeros((n_groups, 8), dtype=torch.int64, device=res.device)
+    g = None if group is None else group.to(torch.int32).contiguous()
+    bank.ber_stats(res, n_frames, wl.tx_bits, wl.lead, wl.gap, cnt, group=g, n_groups=n_groups)
+    if comm is not None:
+        comm.all_reduce_counters(cnt)
+    torch.cuda.synchronize(res.device)
+    c = cnt.cpu().numpy()
+    return {name: c[:, k].copy() for k, name in enumerate(("calls", "valid", "aligned", "bits", "errors"))}

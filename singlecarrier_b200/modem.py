@@ -18,7 +18,9 @@ FRAME_SIZE = 1880
 SYMBOLS_PER_FRAME = 376
 BITS_PER_CALL = 62
 PACKET_SAMPLES = 1880
-OPT_SLAB_PARTS, OPT_PROFILE = 1, 2
+OPT_SLAB_PARTS, OPT_PROFILE, OPT_H2D_MODE = 1, 2, 3
+H2D_COLUMNS, H2D_ROWS, H2D_FULL, H2D_COLUMNS_3D = 0, 1, 2, 3
+N_COUNTERS, N_BER_COUNTERS = 16, 8
 REFERENCE_GAP = 903         # dead air between packets in the reference's main(), qpsk.c:410-412
 
 # sc_frame_result, include/singlecarrier_b200.h
@@ -44,6 +46,81 @@ def unpack_bits(results: np.ndarray, rows: Optional[np.ndarray] = None) -> np.nd
         rows = np.full(r.shape + (BITS_PER_CALL,), 255, np.uint8)
     lib.sc_unpack_bits(r.ctypes.data, r.size, rows.ctypes.data)
     return rows
+
+
+class PinnedBuffer:
+    """Page-locked host memory on the NUMA node of ``device`` (sc_host_alloc); ``array(dtype, shape)``
+    gives numpy views.  Freed by ``close()`` / garbage collection."""
+
+    def __init__(self, nbytes: int, device: int = 0):
+        self._p = C.c_void_p()
+        node = C.c_int(-1)
+        check(lib.sc_host_alloc(C.byref(self._p), nbytes, device, C.byref(node)))
+        self.nbytes, self.numa_node = nbytes, node.value
+
+    def array(self, dtype, shape, offset: int = 0) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        assert offset + count * dtype.itemsize <= self.nbytes
+        buf = (C.c_char * (count * dtype.itemsize)).from_address(self._p.value + offset)
+        a = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+        a.flags.writeable = True
+        return a
+
+    def close(self) -> None:
+        if self._p:
+            lib.sc_host_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def h2d_probe(device: int, buffer_bytes: int, row_bytes: int = 0, src_pitch_bytes: int = 0, min_seconds: float = 0.5,
+              d2h: bool = False) -> float:
+    """GB/s of plain pinned-host <-> device copies (sc_h2d_probe): the platform ceiling of the host entry point."""
+    out = C.c_double(0.0)
+    check(lib.sc_h2d_probe(device, buffer_bytes, row_bytes, src_pitch_bytes, min_seconds, int(d2h), C.byref(out)))
+    return out.value
+
+
+class NcclComm:
+    """A ncclComm_t created through the library's NCCL bridge (sc_comm_*)."""
+
+    def __init__(self, handle):
+        self._c = handle
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(lib.sc_comm_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def init_rank(cls, n_ranks: int, rank: int, unique_id: bytes, device: int) -> "NcclComm":
+        h = C.c_void_p()
+        check(lib.sc_comm_init_rank(C.byref(h), n_ranks, rank, unique_id, device))
+        return cls(h)
+
+    @classmethod
+    def init_all(cls, devices) -> list:
+        n = len(devices)
+        arr = (C.c_void_p * n)()
+        devs = (C.c_int * n)(*devices)
+        check(lib.sc_comm_init_all(arr, n, devs))
+        return [cls(C.c_void_p(arr[i])) for i in range(n)]
+
+    def all_reduce_counters(self, counters, stream: int = 0) -> None:
+        """In-place sum of a CUDA int64/uint64 tensor over the communicator (sc_reduce_stats)."""
+        check(lib.sc_reduce_stats(counters.data_ptr(), counters.numel(), self._c, stream))
+
+    def close(self) -> None:
+        if self._c:
+            lib.sc_comm_destroy(self._c)
+            self._c = C.c_void_p()
 
 
 def _ptr(t) -> int:
@@ -101,6 +178,31 @@ class ModemBank:
         """Accumulate the 16 lock/bit counters of results (CUDA uint8 [n, >= n_frames*32]) into counters (CUDA int64[16])."""
         check(lib.sc_lock_stats_dev(self.device, results.data_ptr(), self.n_streams, results.stride(0) // 32, n_frames,
                                     counters.data_ptr(), stream))
+
+    def ber_stats(self, results, n_frames: int, tx_bits, lead_in, gap: int, counters, group=None, n_groups: int = 1,
+                  stream: int = 0) -> None:
+        """Accumulate the bit-error counters (sc_ber_stats_dev) of a cold-started batch into counters
+        (CUDA int64 [n_groups, 8]): calls, valid, aligned, bits, errors."""
+        n_packets = tx_bits.shape[1]
+        check(lib.sc_ber_stats_dev(self.device, results.data_ptr(), self.n_streams, results.stride(0) // 32, n_frames,
+                                   tx_bits.data_ptr(), n_packets, _ptr(lead_in), gap, _ptr(group), n_groups,
+                                   counters.data_ptr(), stream))
+
+    def transfer_bytes(self):
+        out = (C.c_uint64 * 2)()
+        check(lib.sc_transfer_bytes(self._h, out))
+        return int(out[0]), int(out[1])
+
+    def state_export(self) -> np.ndarray:
+        """Checkpoint of the whole bank (sc_state_export) as a uint8 array."""
+        n = int(lib.sc_state_size(self._h))
+        buf = np.empty(n, np.uint8)
+        check(lib.sc_state_export(self._h, buf.ctypes.data, n))
+        return buf
+
+    def state_import(self, image: np.ndarray) -> None:
+        image = np.ascontiguousarray(image, np.uint8)
+        check(lib.sc_state_import(self._h, image.ctypes.data, image.size))
 
     # ---- RX ------------------------------------------------------------------------------------
     def rx_frames_host(self, samples: np.ndarray, n_frames: Optional[int] = None, results: Optional[np.ndarray] = None):

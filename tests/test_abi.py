@@ -82,11 +82,43 @@ def test_host_helpers_need_no_gpu():
             o.lib.sco_scramble2(C.byref(d), C.byref(lfsr))
             w |= (d.value & 1) << (2 * i) | (d.value >> 1) << (2 * i + 1)
         assert sc.keystream_word(n) == w
+    # positions beyond one LFSR period (32767 bits = 528.5 calls) are reached by reducing the offset, not by
+    # replaying from the seed: check against a straight replay
+    lfsr = C.c_uint16(0x4A80)
+    want = {}
+    for n in range(1200):
+        w = 0
+        for i in range(31):
+            d = C.c_uint8(0)
+            o.lib.sco_scramble2(C.byref(d), C.byref(lfsr))
+            w |= (d.value & 1) << (2 * i) | (d.value >> 1) << (2 * i + 1)
+        want[n] = w
+    for n in (5, 527, 528, 529, 1056, 1057, 1199):
+        assert sc.keystream_word(n) == want[n], n
+    assert sc.keystream_word(32767 * 3 + 11) == want[11]           # 62 * 32767 bits = a whole number of periods
     r = np.zeros(3, sc.RESULT_DTYPE)
     r["bits"] = [0b1011, 0x3FFFFFFFFFFFFFFF, 5]
     r["valid"] = [1, 1, 0]
     rows = sc.unpack_bits(r)
     assert rows[0][:4].tolist() == [1, 1, 0, 1] and rows[1].all() and (rows[2] == 255).all()
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Round-2 entry points: argument errors are reported before any CUDA call; compute refuses without a device."""
+    import torch
+    import singlecarrier_b200 as sc
+    L = sc.lib
+    assert L.sc_state_size(None) == 0
+    assert L.sc_state_export(None, None, 0) == -1 and L.sc_state_import(None, None, 0) == -1
+    assert L.sc_reduce_stats(None, 16, None, None) == -1
+    assert L.sc_host_alloc(None, 0, 0, None) == -1 and L.sc_host_free(None) == 0
+    out = C.c_double(0)
+    assert L.sc_h2d_probe(0, 16, 0, 0, 0.0, 0, C.byref(out)) == -1          # buffer too small
+    assert L.sc_ber_stats_dev(0, None, 1, 1, 1, None, 1, None, 0, None, 1, None, None) == -1
+    if not torch.cuda.is_available():
+        assert L.sc_h2d_probe(0, 1 << 20, 0, 0, 0.0, 0, C.byref(out)) == -2
+        p = C.c_void_p()
+        assert L.sc_host_alloc(C.byref(p), 4096, 0, None) == -2
 
 
 def test_product_never_imports_the_oracle():

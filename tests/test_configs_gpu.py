@@ -33,6 +33,18 @@ def check_subset(sc, oracle, wl, res, n_frames, idx):
     assert alone.tobytes() == r.tobytes()
 
 
+def assert_device_ber_equals_harness(bank, res, n_frames, wl, st, group=None, n_groups=1):
+    """sc_ber_stats_dev (packet alignment + error count in one kernel) == the torch-op recount of harness.py."""
+    import torch
+    cnt = torch.zeros((n_groups, 8), dtype=torch.int64, device=res.device)
+    bank.ber_stats(res, n_frames, wl.tx_bits, wl.lead, wl.gap, cnt, group=group, n_groups=n_groups)
+    torch.cuda.synchronize()
+    c = cnt.cpu().numpy()
+    for k, name in enumerate(("calls", "valid", "aligned", "bits", "errors")):
+        assert c[:, k].tolist() == st[name].tolist(), (name, c[:, k], st[name])
+    assert (c[:, 5:] == 0).all()
+
+
 def test_config2_1024_loopback_streams_clean_channel(sc, oracle):
     from singlecarrier_b200 import harness
     ns, nf = 1024, 11
@@ -51,6 +63,7 @@ def test_config2_1024_loopback_streams_clean_channel(sc, oracle):
     assert st["valid"][0] > ns and st["aligned"][0] > 0.5 * st["valid"][0]
     # the reference's equalizer diverges (BER ~0.30 even with no offset); with +-20 Hz it is worse
     assert 0.15 < st["errors"][0] / st["bits"][0] < 0.55
+    assert_device_ber_equals_harness(bank, res, nf, wl, st)
     bank.close()
 
 
@@ -65,6 +78,7 @@ def test_config3_65536_streams_awgn_sweep_ber_curve(sc, oracle):
     assert torch.equal(res, res2)                                              # deterministic
     group = (torch.arange(ns, device="cuda") % 13)
     st = harness.ber_and_lock(res, nf, wl, group=group, n_groups=13)
+    assert_device_ber_equals_harness(bank, res, nf, wl, st, group=group.int(), n_groups=13)
     lock = st["valid"] / st["calls"]
     ber = st["errors"] / np.maximum(st["bits"], 1)
     print("Eb/N0 0..12 dB lock rate", np.round(lock, 4).tolist(), "BER", np.round(ber, 3).tolist())
@@ -93,8 +107,9 @@ def test_config5_262144_streams_drift_multipath(sc, oracle):
     st = harness.ber_and_lock(res, nf, wl)
     assert st["valid"][0] > 0.02 * st["calls"][0]
     rng = np.random.default_rng(1)
-    idx = np.sort(rng.choice(ns, 768, replace=False))
+    idx = np.sort(rng.choice(ns, 4096, replace=False))                          # 4,096-stream subset
     check_subset(sc, oracle, wl, res, nf, idx)
+    assert_device_ber_equals_harness(bank, res, nf, wl, st)
     bank.close()
 
 
@@ -113,7 +128,7 @@ def test_host_entry_point_matches_device_entry_point_large(sc):
 
 def test_config4_per_gpu_shard_131072_streams_10s(sc, oracle):
     """bench.py's workload (config 4 sharded: 131,072 streams x 42 calls, 21 GB of samples): oracle on a
-    1,024-stream subset, results independent of the slab split, counters consistent."""
+    4,096-stream subset, results independent of the slab split, device bit-error counters == host recount."""
     import torch
     from singlecarrier_b200 import harness
     from singlecarrier_b200.modem import OPT_SLAB_PARTS
@@ -126,9 +141,10 @@ def test_config4_per_gpu_shard_131072_streams_10s(sc, oracle):
     assert torch.equal(res, res5)
     bank.set_option(OPT_SLAB_PARTS, 0)
     rng = np.random.default_rng(4)
-    idx = np.sort(rng.choice(ns, 1024, replace=False))
+    idx = np.sort(rng.choice(ns, 4096, replace=False))                          # 4,096-stream subset
     check_subset(sc, oracle, wl, res, nf, idx)
     st = harness.ber_and_lock(res, nf, wl)
+    assert_device_ber_equals_harness(bank, res, nf, wl, st)
     cnt = torch.zeros(16, dtype=torch.int64, device="cuda")
     bank.lock_stats(res, nf, cnt)
     torch.cuda.synchronize()

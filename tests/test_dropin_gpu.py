@@ -110,6 +110,24 @@ def test_legacy_l1_symbols_via_ctypes(gold):
     assert np.array_equal(spec.view(np.uint32), f["r64_spec"].view(np.uint32))
 
 
+def test_interleaved_globals_match_reference(ref):
+    """qpsk_rx_frame() shares RXMemory with scramble()/scramble_init()/data_eq() and leaves eq_coeff,
+    kalman_gain, kalman_y and the internal u/d behind (src/scramble.c:41-42, src/equalizer.c:87,
+    src/kalman.c:19-35): a caller that interleaves them sees exactly what the reference's objects give."""
+    import sys
+    from oracle import pyoracle as po
+    raw = os.path.join(ROOT, "tests", "golden", "preamble_qpsk_8k.raw")
+    drv = os.path.join(ROOT, "tests", "dropin_interleave.py")
+    ours = os.path.join(ROOT, "singlecarrier_b200", "libsinglecarrier_b200.so")
+    a = subprocess.run([sys.executable, drv, po.REF_SO, raw, "ref"], check=True, capture_output=True, text=True, timeout=300)
+    b = subprocess.run([sys.executable, drv, ours, raw, "ours"], check=True, capture_output=True, text=True, timeout=300)
+    la, lb = a.stdout.strip().splitlines(), b.stdout.strip().splitlines()
+    assert len(la) == len(lb) == 14 + 4
+    for x, y in zip(la, lb):
+        assert x == y
+    assert '"valid": 1' in la[15] and '"call": 12' in la[15]     # the locked frame is part of the sequence
+
+
 def test_legacy_tx_frame_arbitrary_symbols(oracle):
     """qpsk_tx_frame() with symbols that are not +-1 (general 49-tap path, filter memory and phasor carried
     across calls) against the oracle's restatement."""

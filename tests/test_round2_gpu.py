@@ -1,0 +1,240 @@
+"""GPU: round-2 additions -- parity against the reference's OWN objects on the GPU box, the host-path copy
+modes, checkpoint/resume, the warp-shuffle FFT, stream-ordered FFT scratch, the device counters and the
+NCCL reduction in the C ABI."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import synth_streams
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def sc():
+    import singlecarrier_b200 as m
+    assert m.lib.sc_device_count() > 0, "no CUDA device"
+    return m
+
+
+def test_cuda_path_vs_reference_objects_directly(sc, ref, oracle, gold):
+    """CUDA <-> oracle/_ref/libsc_ref.so (the reference's own .c files compiled by oracle/Makefile) with no
+    restatement in between: the shipped file plus 64 noisy loop-back streams."""
+    x = gold("preamble_qpsk_8k.raw")
+    shipped = np.zeros((1, 14 * 1880), np.int16)
+    shipped[0] = x[: 14 * 1880]
+    rng = np.random.default_rng(2024)
+    noisy = synth_streams(oracle, rng, 64, 14)                 # oracle TX is only the signal source here
+    samples = np.concatenate([shipped, noisy])
+    bank = sc.ModemBank(samples.shape[0], debug_eq=True)
+    res, eq = bank.rx_frames_host(samples, 14)
+    bank.close()
+    rows = sc.unpack_bits(res)
+    n_valid = 0
+    for s in range(samples.shape[0]):
+        rbits, rst = ref.run_stream(samples[s])
+        assert res["valid"][s].astype(np.int32).tolist() == rst["valid"].tolist(), s
+        assert res["max_index"][s].astype(np.int32).tolist() == rst["max_index"].tolist(), s
+        assert res["rx_timing"][s].astype(np.int32).tolist() == rst["rx_timing"].tolist(), s
+        assert np.array_equal(res["max_value"][s].view(np.uint32), rst["max_value"].view(np.uint32)), s
+        assert np.array_equal(eq[s].view(np.uint32), np.ascontiguousarray(rst["eq_coeff"]).view(np.uint32)), s
+        v = rst["valid"].astype(bool)
+        assert np.array_equal(rows[s][v], rbits[v]), s
+        # matches / Mean only exist in the reference's DEBUG2 printf of valid frames (qpsk.c:198)
+        assert res["matches"][s][v].astype(np.int32).tolist() == rst["matches"][v].tolist(), s
+        assert np.array_equal(res["cost"][s][v].view(np.uint32), rst["mean"][v].view(np.uint32)), s
+        n_valid += int(v.sum())
+    assert n_valid > 100
+
+
+@pytest.mark.parametrize("extra_stride", [0, 1880, 246])
+def test_h2d_modes_give_identical_results(sc, oracle, extra_stride):
+    """SC_H2D_COLUMNS / ROWS / FULL / COLUMNS_3D move different bytes but never a different result; the byte
+    counters report what was queued."""
+    from singlecarrier_b200.modem import H2D_COLUMNS, H2D_COLUMNS_3D, H2D_FULL, H2D_ROWS, OPT_H2D_MODE, OPT_SLAB_PARTS
+    rng = np.random.default_rng(5)
+    ns, nf = 300, 7
+    dense = synth_streams(oracle, rng, ns, nf)
+    wide = np.zeros((ns, nf * 1880 + extra_stride), np.int16)
+    wide[:, : nf * 1880] = dense
+    got = {}
+    for mode in (H2D_COLUMNS, H2D_ROWS, H2D_FULL, H2D_COLUMNS_3D):
+        for parts in (0, 3):
+            bank = sc.ModemBank(ns)
+            bank.set_option(OPT_H2D_MODE, mode)
+            bank.set_option(OPT_SLAB_PARTS, parts)
+            res, _ = bank.rx_frames_host(wide, nf)
+            h2d, d2h = bank.transfer_bytes()
+            bank.close()
+            got[(mode, parts)] = res.tobytes()
+            assert d2h == ns * nf * 32
+            if mode == H2D_FULL:
+                assert h2d == ns * nf * 3760
+            elif mode in (H2D_COLUMNS, H2D_COLUMNS_3D):
+                assert h2d == ns * nf * 1624 * 2
+            else:
+                assert ns * nf * 1624 * 2 < h2d < ns * nf * 3760
+    first = got[(H2D_COLUMNS, 0)]
+    assert all(v == first for v in got.values())
+
+
+def test_pinned_buffer_and_probe(sc):
+    buf = sc.PinnedBuffer(4 * 1880 * 2 * 10, device=0)
+    a = buf.array(np.int16, (10, 4 * 1880))
+    a[:] = 0
+    bank = sc.ModemBank(10)
+    res, _ = bank.rx_frames_host(a, 4)
+    bank.close()
+    assert res["valid"][:, :2].all()                             # silence is "valid" for the first two calls (F6)
+    buf.close()
+    gbs = sc.h2d_probe(0, 64 << 20, min_seconds=0.05)
+    gbs2d = sc.h2d_probe(0, 64 << 20, row_bytes=3248, src_pitch_bytes=157920, min_seconds=0.05)
+    assert gbs > 1.0 and gbs2d > 1.0
+
+
+def test_state_export_import_resumes_bit_exactly(sc, oracle):
+    """Checkpoint after 5 calls, continue in a NEW bank: identical to the uninterrupted run."""
+    rng = np.random.default_rng(77)
+    ns, nf = 130, 12
+    samples = synth_streams(oracle, rng, ns, nf)
+    a = sc.ModemBank(ns, debug_eq=True)
+    whole, eq_whole = a.rx_frames_host(samples, nf)
+    a.close()
+    b = sc.ModemBank(ns, debug_eq=True)
+    first, _ = b.rx_frames_host(samples[:, : 5 * 1880].copy(), 5)
+    image = b.state_export()
+    b.close()
+    assert first.tobytes() == whole[:, :5].tobytes()
+    c = sc.ModemBank(ns, debug_eq=True)
+    c.state_import(image)
+    assert c.call_index == 5
+    rest, eq_rest = c.rx_frames_host(samples[:, 5 * 1880:].copy(), nf - 5)
+    c.close()
+    assert rest.tobytes() == np.ascontiguousarray(whole[:, 5:]).tobytes()
+    assert np.array_equal(eq_rest.view(np.uint32), np.ascontiguousarray(eq_whole[:, 5:]).view(np.uint32))
+    d = sc.ModemBank(ns + 1)
+    with pytest.raises(sc.SingleCarrierError):
+        d.state_import(image)                                     # another bank size: refused
+    d.close()
+
+
+def test_fft256_warp_kernel_large_batch(sc):
+    """The register / warp-shuffle n=256 kernel (out of place) against the generic shared-memory kernel (taken
+    for in-place calls), bit for bit, over a batch larger than the persistent grid; both directions."""
+    import torch
+    rng = np.random.default_rng(3)
+    nb = 148 * 12 * 4 * 2 + 37
+    x = (rng.normal(size=(nb, 256)) + 1j * rng.normal(size=(nb, 256))).astype(np.complex64)
+    x[5] = 0
+    x[6, 1:] = 0
+    for inv in (0, 1):
+        d_in = torch.from_numpy(x.view(np.float32)).cuda()
+        d_out = torch.zeros_like(d_in)
+        sc._lib.check(sc.lib.sc_fft_batch_dev(0, nb, 256, inv, d_in.data_ptr(), d_out.data_ptr(), 0))
+        d_ip = d_in.clone()
+        sc._lib.check(sc.lib.sc_fft_batch_dev(0, nb, 256, inv, d_ip.data_ptr(), d_ip.data_ptr(), 0))
+        torch.cuda.synchronize()
+        assert torch.equal(d_out.view(torch.int32), d_ip.view(torch.int32))
+        y = d_out.cpu().numpy().view(np.complex64)
+        want = np.fft.ifft(x[:64].astype(np.complex128), axis=1) * 256 if inv else np.fft.fft(x[:64].astype(np.complex128), axis=1)
+        assert np.abs(y[:64] - want).max() <= 1e-5 * np.abs(want).max() * 8
+
+
+def test_fft_two_streams_do_not_share_scratch(sc):
+    """Transforms too long for shared memory use stream-ordered scratch per call: two n=8192 batches queued on two
+    CUDA streams at once give the results of running them one after the other."""
+    import torch
+    rng = np.random.default_rng(8)
+    n, nb = 8192, 96
+    xa = torch.from_numpy((rng.normal(size=(nb, n, 2))).astype(np.float32)).cuda()
+    xb = torch.from_numpy((rng.normal(size=(nb, n, 2))).astype(np.float32)).cuda()
+    ya, yb = torch.zeros_like(xa), torch.zeros_like(xb)
+    sc._lib.check(sc.lib.sc_fft_batch_dev(0, nb, n, 0, xa.data_ptr(), ya.data_ptr(), 0))
+    sc._lib.check(sc.lib.sc_fft_batch_dev(0, nb, n, 0, xb.data_ptr(), yb.data_ptr(), 0))
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        za, zb = torch.zeros_like(xa), torch.zeros_like(xb)
+        torch.cuda.synchronize()
+        sc._lib.check(sc.lib.sc_fft_batch_dev(0, nb, n, 0, xa.data_ptr(), za.data_ptr(), s1.cuda_stream))
+        sc._lib.check(sc.lib.sc_fft_batch_dev(0, nb, n, 0, xb.data_ptr(), zb.data_ptr(), s2.cuda_stream))
+        torch.cuda.synchronize()
+        assert torch.equal(za, ya) and torch.equal(zb, yb)
+    sc._lib.check(sc.lib.sc_release_caches())
+    zc = torch.zeros_like(xa)
+    sc._lib.check(sc.lib.sc_fft_batch_dev(0, nb, n, 0, xa.data_ptr(), zc.data_ptr(), 0))   # tables are rebuilt
+    torch.cuda.synchronize()
+    assert torch.equal(zc, ya)
+
+
+def test_lock_stats_field_decoding_stride_and_bin_clamp(sc):
+    """lock_stats_kernel against a numpy recount on hand-made records: result_stride > n_frames, matches up to
+    128 (bin clamp at 7), all 16 counters."""
+    import torch
+    from test_multiprocess import counters_from_results
+    rng = np.random.default_rng(12)
+    ns, nf, stride = 517, 7, 11
+    rec = np.zeros((ns, stride), sc.RESULT_DTYPE)
+    rec["valid"] = rng.integers(0, 2, (ns, stride))
+    rec["matches"] = rng.integers(0, 129, (ns, stride))
+    rec["matches"][0, :nf] = 128
+    rec["max_index"] = rng.integers(0, 128, (ns, stride))
+    rec["rx_timing"] = rng.integers(3, 256, (ns, stride))
+    rec["bits"] = rng.integers(0, 2 ** 62, (ns, stride), dtype=np.uint64)
+    d = torch.from_numpy(rec.view(np.uint8).reshape(ns, stride * 32)).cuda()
+    cnt = torch.zeros(16, dtype=torch.int64, device="cuda")
+    sc._lib.check(sc.lib.sc_lock_stats_dev(0, d.data_ptr(), ns, stride, nf, cnt.data_ptr(), 0))
+    torch.cuda.synchronize()
+    r = rec[:, :nf]
+    want = counters_from_results(r["valid"], r["matches"].astype(np.int64), r["max_index"].astype(np.int64),
+                                 r["rx_timing"].astype(np.int64), r["bits"])
+    assert cnt.cpu().numpy().tolist() == want.tolist()
+
+
+def test_reduce_stats_through_the_c_abi(sc, oracle):
+    """sc_reduce_stats on communicators made by the library's NCCL bridge: one rank (identity) always; with two
+    or more GPUs, two banks on devices 0 and 1 reduce to the single-bank counters."""
+    import torch
+    rng = np.random.default_rng(31)
+    ns, nf = 64, 6
+    samples = synth_streams(oracle, rng, ns, nf)
+
+    def counters(dev, lo, hi):
+        torch.cuda.set_device(dev)
+        bank = sc.ModemBank(hi - lo, device=dev)
+        d_in = torch.from_numpy(samples[lo:hi]).cuda(dev)
+        d_res = torch.zeros((hi - lo, nf * 32), dtype=torch.uint8, device=f"cuda:{dev}")
+        bank.rx_frames_dev(d_in, nf, d_res)
+        cnt = torch.zeros(16, dtype=torch.int64, device=f"cuda:{dev}")
+        bank.lock_stats(d_res, nf, cnt)
+        torch.cuda.synchronize(dev)
+        bank.close()
+        return cnt
+
+    whole = counters(0, 0, ns)
+    comm = sc.NcclComm.init_all([0])[0]
+    one = whole.clone()
+    comm.all_reduce_counters(one)
+    torch.cuda.synchronize()
+    comm.close()
+    assert torch.equal(one, whole) and int(whole[0]) == ns * nf
+    if torch.cuda.device_count() >= 2:
+        parts = [counters(0, 0, ns // 2), counters(1, ns // 2, ns)]
+        comms = sc.NcclComm.init_all([0, 1])
+        # one process drives both ranks: the two collective calls must be grouped
+        nccl = C.CDLL("libnccl.so.2")
+        nccl.ncclGroupStart()
+        for dev, (cm, p) in enumerate(zip(comms, parts)):
+            torch.cuda.set_device(dev)
+            cm.all_reduce_counters(p)
+        nccl.ncclGroupEnd()
+        for dev in (0, 1):
+            torch.cuda.synchronize(dev)
+        assert parts[0].cpu().tolist() == whole.cpu().tolist() == parts[1].cpu().tolist()
+        for cm in comms:
+            cm.close()
+        torch.cuda.set_device(0)

@@ -58,6 +58,18 @@ want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 stall = [k for k in h if "issue_stalled" in k and k.endswith("per_issue_active.ratio")]
+
+# compact, committed copy of the raw page: what bench.py's roofline.traffic is parsed from
+git = subprocess.run(["git", "rev-parse", "--short", "HEAD"], cwd=ROOT, capture_output=True, text=True).stdout.strip()
+with open(os.path.join(out_dir, f"{rnd}_ncu_raw.csv"), "w") as f:
+    w = csv.writer(f)
+    w.writerow(["# ncu --set full --clock-control none --import-source on; ncu -i prof.ncu-rep --page raw --csv; git", git])
+    w.writerow(["kernel", "grid", "block", "metric", "unit", "value"])
+    for r in data:
+        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").strip()
+        for k in want + stall:
+            if k in idx and r[idx[k]] not in ("", "n/a"):
+                w.writerow([name, r[idx["Grid Size"]], r[idx["Block Size"]], k, units[idx[k]], r[idx[k]].replace(",", "")])
 with open(os.path.join(out_dir, f"{rnd}_ncu_summary.md"), "w") as f:
     f.write(f"# {rnd}: `ncu --set full --clock-control none` of the two RX kernels at full launch size\n\n"
             "Command: `python bench.py --streams 131072 --seconds 1 --steps 1 --warmup 3 --no-e2e --no-cpu --slab-parts 1`\n"
