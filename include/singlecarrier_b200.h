@@ -192,10 +192,17 @@ int sc_fir_batch_dev(int device, int64_t n_streams, int wide, float *memory, flo
                      int64_t sample_stride, int length, void *stream);
 
 /* correlate() + argmax, qpsk.c:88-96,172-183: symbols[s*symbol_stride .. +255) complex float
- * -> max_index[s], max_value[s]. */
+ * -> max_index[s], max_value[s].  Two kernels, identical results to the last bit:
+ *   sc_preamble_search_batch_dev         all 128 correlations are PROPOSED on the tensor cores (bf16 split of the
+ *                                        operands, fp32 accumulation, rigorous error bound), then only the lags that
+ *                                        can be the maximum are evaluated with the reference's exact sequential sums;
+ *   sc_preamble_search_direct_batch_dev  every lag with the exact sums (the form the RX chain fuses). */
 int sc_preamble_search_batch_dev(int device, int64_t n_streams, const float *symbols,
                                  int64_t symbol_stride, int32_t *max_index, float *max_value,
                                  void *stream);
+int sc_preamble_search_direct_batch_dev(int device, int64_t n_streams, const float *symbols,
+                                        int64_t symbol_stride, int32_t *max_index, float *max_value,
+                                        void *stream);
 
 /* kalman_reset() + equalize() + the data_eq() loop, qpsk.c:186-236: the decision half of one
  * qpsk_rx_frame() call on an explicit symbol window.  symbols[s*symbol_stride .. +290) complex

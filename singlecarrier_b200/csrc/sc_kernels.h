@@ -30,6 +30,9 @@ cudaError_t launch_fir_batch(bool wide, long n_streams, float2 *memory, float2 *
                              int length, cudaStream_t st, bool fast = false);
 cudaError_t launch_search_batch(long n_streams, const float2 *symbols, long symbol_stride, int *max_index,
                                 float *max_value, cudaStream_t st);
+void search_mma_make_table(uint32_t *table /* [9][32][4] */);
+cudaError_t launch_search_mma_batch(long n_streams, const float2 *symbols, long symbol_stride, const void *a_table,
+                                    int *max_index, float *max_value, cudaStream_t st);
 cudaError_t launch_track_window_batch(long n_streams, const float2 *symbols, long symbol_stride,
                                       const int *max_index, const float *max_value, int *rx_timing,
                                       uint32_t call_index, unsigned long long keystream,

@@ -7,6 +7,7 @@
 #include "sc_tables.cuh"
 #include "sc_tracker.cuh"
 #include "sc_search.cuh"
+#include "sc_search_mma.cuh"
 #include "sc_track_core.cuh"
 #include "sc_kernels.h"
 
@@ -121,6 +122,89 @@ search_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride, int 
             max_value[s] = bv;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same search with the tensor-core proposer (sc_search_mma.cuh): one warp per PAIR of windows.
+// ------------------------------------------------------------------------------------------------
+constexpr int SMM_WARPS = 4;
+
+__global__ void __launch_bounds__(SMM_WARPS * 32, 6)
+search_mma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride, const uint4 *__restrict__ a_table,
+                        int *__restrict__ max_index, float *__restrict__ max_value, long n_streams) {
+    __shared__ __align__(16) SearchMmaSmem sm_all[SMM_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    SearchMmaSmem &sm = sm_all[warp];
+    const long n_pairs = (n_streams + 1) / 2;
+    for (long pr = (long) blockIdx.x * SMM_WARPS + warp; pr < n_pairs; pr += (long) gridDim.x * SMM_WARPS) {
+        float s_abs[2];
+        __syncwarp();
+        // all 16 loads of the pair are in flight before anything is staged
+        float2 v0[2][4], v1[2][4];
+#pragma unroll
+        for (int w = 0; w < 2; w++) {
+            const long s = 2 * pr + w;
+            const float2 *x = symbols + s * symbol_stride;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {                      // symbol pairs (xx, xx + 1), xx = 2 lane + 64 k
+                const int xx = 2 * lane + 64 * k;
+                v0[w][k] = v1[w][k] = make_float2(0.0f, 0.0f);
+                if (s < n_streams) {
+                    v0[w][k] = x[xx];
+                    if (xx + 1 < SEARCH_SYMS) v1[w][k] = x[xx + 1];
+                }
+            }
+        }
+        float part[2] = {0.0f, 0.0f};
+#pragma unroll
+        for (int w = 0; w < 2; w++)
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                part[w] = __fadd_rn(part[w], search_mma_stage_pair(sm, w, 2 * lane + 64 * k, v0[w][k], v1[w][k]));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            part[0] = __fadd_rn(part[0], __shfl_xor_sync(0xffffffffu, part[0], off));
+            part[1] = __fadd_rn(part[1], __shfl_xor_sync(0xffffffffu, part[1], off));
+        }
+        s_abs[0] = part[0];
+        s_abs[1] = part[1];
+        __syncwarp();
+        int bi[2];
+        float bv[2];
+        search_mma_pair(sm, a_table, lane, s_abs, bi, bv);
+        if (lane < 2 && 2 * pr + lane < n_streams) {
+            max_index[2 * pr + lane] = lane ? bi[1] : bi[0];
+            max_value[2 * pr + lane] = lane ? bv[1] : bv[0];
+        }
+    }
+}
+
+// A fragments of the 9 Toeplitz tiles (sc_search_mma.cuh), host side
+void search_mma_make_table(uint32_t *table /* [9][32][4] */) {
+    auto val = [](int t, int r, int c) -> uint32_t {
+        const int i = 16 * t + c - r;
+        if (i < 0 || i >= PRE) return 0u;
+        return preamble_value(i) < 0 ? 0xBF80u : 0x3F80u;                // bf16 -1.0 / +1.0
+    };
+    for (int t = 0; t < SM_TILES; t++)
+        for (int lane = 0; lane < 32; lane++) {
+            const int g = lane >> 2, tid = lane & 3;
+            uint32_t *o = table + ((size_t) t * 32 + lane) * 4;
+            o[0] = val(t, g, 2 * tid) | (val(t, g, 2 * tid + 1) << 16);
+            o[1] = val(t, g + 8, 2 * tid) | (val(t, g + 8, 2 * tid + 1) << 16);
+            o[2] = val(t, g, 2 * tid + 8) | (val(t, g, 2 * tid + 9) << 16);
+            o[3] = val(t, g + 8, 2 * tid + 8) | (val(t, g + 8, 2 * tid + 9) << 16);
+        }
+}
+
+cudaError_t launch_search_mma_batch(long n_streams, const float2 *symbols, long symbol_stride, const void *a_table,
+                                    int *max_index, float *max_value, cudaStream_t st) {
+    const long n_pairs = (n_streams + 1) / 2;
+    const int grid = (int) std::min<long>((n_pairs + SMM_WARPS - 1) / SMM_WARPS, 148L * 6);     // one resident wave
+    search_mma_batch_kernel<<<grid, SMM_WARPS * 32, 0, st>>>(symbols, symbol_stride, (const uint4 *) a_table, max_index,
+                                                             max_value, n_streams);
+    g_launch_count++;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_search_batch(long n_streams, const float2 *symbols, long symbol_stride, int *max_index,

@@ -238,3 +238,47 @@ def test_reduce_stats_through_the_c_abi(sc, oracle):
         for cm in comms:
             cm.close()
         torch.cuda.set_device(0)
+
+
+def test_tensor_core_proposed_search_equals_direct_search(sc, oracle):
+    """sc_preamble_search_batch_dev (tensor-core proposer + exact verifier) against the all-exact kernel, bit for
+    bit, on 200k windows built to stress the candidate logic: noise only, planted preambles at every lag, several
+    equal maxima (ties), silence, one non-zero symbol, tiny and huge amplitudes, a window repeated with a one-ulp
+    change, and odd window counts / strides."""
+    import torch
+    pv = np.frombuffer((C.c_int8 * 128).in_dll(oracle.lib, "sco_preamblevalues"), np.int8).astype(np.float32)
+    rng = np.random.default_rng(42)
+    for ns, stride in ((200001, 255), (777, 260)):
+        sym = (rng.normal(size=(ns, stride)) + 1j * rng.normal(size=(ns, stride))).astype(np.complex64)
+        k = min(ns - 500, 4000)
+        for s in range(0, k):                                   # planted preambles, every lag, various SNR
+            lag = s % 128
+            sym[s, lag:lag + 128] += (np.float32(0.2 + (s % 7)) * pv * (1 + 1j)).astype(np.complex64)
+        sym[k:k + 50] = 0                                       # silence -> (0, 0.0)
+        for s in range(k + 50, k + 100):                        # a single non-zero symbol: many lags tie
+            sym[s] = 0
+            sym[s, 100 + (s % 100)] = 1 + 1j
+        for s in range(k + 100, k + 150):                       # two planted preambles of equal strength, no noise
+            sym[s] = 0
+            a, b = (s * 3) % 60, 64 + (s * 5) % 60
+            sym[s, a:a + 128] += (pv * (1 + 1j)).astype(np.complex64)
+            sym[s, b:b + 128] += (pv * (1 + 1j)).astype(np.complex64)
+        sym[k + 150:k + 250] *= np.float32(1e-6)                # tiny
+        sym[k + 250:k + 350] *= np.float32(3e4)                 # int16-scale and beyond
+        sym[k + 350:k + 400] = sym[k + 400:k + 450]             # near duplicates ...
+        sym[k + 350:k + 400, 77] = np.nextafter(sym[k + 400:k + 450, 77].real, np.float32(9)) + 1j * sym[k + 400:k + 450, 77].imag
+        d = torch.from_numpy(sym.view(np.float32)).cuda()
+        out = {}
+        for name in ("sc_preamble_search_batch_dev", "sc_preamble_search_direct_batch_dev"):
+            idx = torch.full((ns,), -7, dtype=torch.int32, device="cuda")
+            val = torch.full((ns,), -7.0, dtype=torch.float32, device="cuda")
+            sc._lib.check(getattr(sc.lib, name)(0, ns, d.data_ptr(), stride, idx.data_ptr(), val.data_ptr(), 0))
+            torch.cuda.synchronize()
+            out[name] = (idx.cpu().numpy(), val.cpu().numpy())
+        (ai, av), (bi, bv) = out["sc_preamble_search_batch_dev"], out["sc_preamble_search_direct_batch_dev"]
+        bad = np.nonzero((ai != bi) | (av.view(np.uint32) != bv.view(np.uint32)))[0]
+        assert bad.size == 0, (bad[:10], ai[bad[:10]], bi[bad[:10]], av[bad[:10]], bv[bad[:10]])
+        assert (ai[:k] == np.arange(k) % 128)[np.arange(k) % 7 >= 2].mean() > 0.99       # strong preambles are found
+        for s in list(range(0, 40)) + list(range(k, k + 150, 7)):                          # and both equal the oracle
+            oi, ov = oracle.search(sym[s])
+            assert ai[s] == oi and av[s].view(np.uint32) == np.float32(ov).view(np.uint32), s

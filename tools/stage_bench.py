@@ -49,7 +49,10 @@ idx = torch.empty(ns, dtype=torch.int32, device="cuda")
 val = torch.empty(ns, dtype=torch.float32, device="cuda")
 ms = timeit(lambda: check(L.sc_preamble_search_batch_dev(0, ns, s.data_ptr(), 256, idx.data_ptr(), val.data_ptr(), None)))
 gbs = ns * 2048 / ms / 1e6
-rows.append(("search_batch_kernel (correlate + argmax, exact)", f"{ns} windows", ms, gbs, gbs / peak, f"{ns * 33152 / ms / 1e9:.1f} Tops/s of 37.2"))
+rows.append(("search_mma_batch_kernel (tensor-core proposer + exact verifier)", f"{ns} windows", ms, gbs, gbs / peak, "-"))
+ms = timeit(lambda: check(L.sc_preamble_search_direct_batch_dev(0, ns, s.data_ptr(), 256, idx.data_ptr(), val.data_ptr(), None)))
+gbs = ns * 2048 / ms / 1e6
+rows.append(("search_batch_kernel (every lag exact)", f"{ns} windows", ms, gbs, gbs / peak, f"{ns * 33152 / ms / 1e9:.1f} Tops/s of 37.2"))
 del s
 # decision loop on explicit windows: 2^18 windows of 290 symbols
 ns = 1 << 18
