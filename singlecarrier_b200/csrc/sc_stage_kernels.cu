@@ -11,6 +11,8 @@
 #include "sc_track_core.cuh"
 #include "sc_kernels.h"
 
+#include <stdlib.h>
+
 namespace sc {
 
 // ------------------------------------------------------------------------------------------------
@@ -30,6 +32,14 @@ constexpr int FIR_WARPS = 8;
 constexpr int FIR_R = 5;
 constexpr int FIR_TILE = 32 * FIR_R;                   // 160
 
+// Tile pipeline of one warp (both modes):
+//   registers  <- global   the NEXT tile's 160 raw samples (5 coalesced 256-byte loads), issued before this
+//                          tile's arithmetic so the DRAM latency hides behind it (cp.async into rotating buffers
+//                          was measured 8 % slower: 8-byte LDGSTS is the less efficient path);
+//   ext[49..]  <- registers, __syncwarp, 49 + 4 LDS.64 and 245 packed multiply-adds per lane;
+//   obuf       <- results  (obuf is ext + 49: every lane has finished reading by then), carry -> ext[0..48];
+//   global     <- obuf     5 coalesced 256-byte stores per warp (a lane's own 5 outputs are 40 bytes apart,
+//                          which would cost five partial-sector stores per 32-byte sector).
 template <bool WIDE, bool FAST>
 __global__ void __launch_bounds__(FIR_WARPS * 32, 4)
 fir_batch_kernel(float2 *__restrict__ memory, float2 *__restrict__ sample, long sample_stride, int length,
@@ -37,19 +47,32 @@ fir_batch_kernel(float2 *__restrict__ memory, float2 *__restrict__ sample, long 
     __shared__ __align__(16) float2 ext_all[FIR_WARPS][NTAPS + FIR_TILE + 7];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2 *ext = ext_all[warp];
+    float2 *obuf = ext + NTAPS;
     for (long s = (long) blockIdx.x * FIR_WARPS + warp; s < n_streams; s += (long) gridDim.x * FIR_WARPS) {
         float2 *mem = memory + s * NTAPS;
         float2 *x = sample + s * sample_stride;
         __syncwarp();
         for (int i = lane; i < NTAPS; i += 32) ext[i] = mem[i];
+        float2 nxt[FIR_R];
+#pragma unroll
+        for (int k = 0; k < FIR_R; k++) {
+            const int j = lane + 32 * k;
+            nxt[k] = j < length ? x[j] : make_float2(0.f, 0.f);
+        }
         for (int t0 = 0; t0 < length; t0 += FIR_TILE) {
             const int n = min(FIR_TILE, length - t0);
-            for (int j = lane; j < n; j += 32) ext[NTAPS + j] = x[t0 + j];
+#pragma unroll
+            for (int k = 0; k < FIR_R; k++) ext[NTAPS + lane + 32 * k] = nxt[k];
             __syncwarp();
+#pragma unroll
+            for (int k = 0; k < FIR_R; k++) {                                    // next tile's loads fly during the math
+                const int j = t0 + FIR_TILE + lane + 32 * k;
+                nxt[k] = j < length ? x[j] : make_float2(0.f, 0.f);
+            }
             u64 acc[FIR_R];
 #pragma unroll
             for (int r = 0; r < FIR_R; r++) acc[r] = 0ull;
-            if (FIR_R * lane < n) {
+            {
                 const u64 *ep = reinterpret_cast<const u64 *>(ext) + FIR_R * lane + 1;
 #pragma unroll
                 for (int j = 0; j < NTAPS + FIR_R - 1; j++) {
@@ -65,36 +88,173 @@ fir_batch_kernel(float2 *__restrict__ memory, float2 *__restrict__ sample, long 
                 }
             }
             // the last 49 raw inputs become the head of the next tile
-            float2 c0 = make_float2(0.f, 0.f), c1 = c0;
-            c0 = ext[n + lane];
+            float2 c0 = ext[n + lane], c1 = make_float2(0.f, 0.f);
             if (lane + 32 < NTAPS) c1 = ext[n + lane + 32];
             __syncwarp();
 #pragma unroll
             for (int r = 0; r < FIR_R; r++) {
-                const int j = FIR_R * lane + r;
-                if (j < n) {
-                    float yr, yi;
-                    unpk(acc[r], yr, yi);
-                    x[t0 + j] = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));
-                }
+                float yr, yi;
+                unpk(acc[r], yr, yi);
+                obuf[FIR_R * lane + r] = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));
             }
             ext[lane] = c0;
             if (lane + 32 < NTAPS) ext[lane + 32] = c1;
             __syncwarp();
+#pragma unroll
+            for (int k = 0; k < FIR_R; k++) {
+                const int j = lane + 32 * k;
+                if (j < n) x[t0 + j] = obuf[j];
+            }
         }
+        __syncwarp();
+        for (int i = lane; i < NTAPS; i += 32) mem[i] = ext[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same pipeline with 10 outputs per lane (tiles of 320) and 128-bit shared-memory loads: each staged
+// sample is then read by 5.8 lanes instead of 10.6, which is what the contracted (FAST) mode needs -- with
+// half the arithmetic per sample it is bound by the shared-memory data pipe (ncu: 90 % at 5 outputs per
+// lane), not by the FP32 pipe.  buf[1 + i] holds ext[i], so that every lane's window (10 lane + 2) and its
+// 10 outputs (50 + 10 lane) start on a 16-byte boundary; lane stride 80 bytes = 5 x 16 is odd in 16-byte
+// units, hence conflict-free for LDS.128 / STS.128.
+// ------------------------------------------------------------------------------------------------
+constexpr int FIR10_WARPS = 4;
+constexpr int FIR10_R = 10;
+constexpr int FIR10_TILE = 32 * FIR10_R;                // 320
+constexpr int FIR10_BUF = 2 + NTAPS + FIR10_TILE + 9;   // 380 slots
+
+// VEC: every stream starts on a 16-byte boundary (checked by the launcher), so global memory is moved two
+// complex samples (128 bits) per lane and instruction; otherwise one sample (64 bits) at a time.
+template <bool WIDE, bool FAST, bool VEC>
+__global__ void __launch_bounds__(FIR10_WARPS * 32, 6)
+fir_batch10_kernel(float2 *__restrict__ memory, float2 *__restrict__ sample, long sample_stride, int length,
+                   long n_streams) {
+    __shared__ __align__(16) float2 buf_all[FIR10_WARPS][FIR10_BUF];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2 *ext = buf_all[warp] + 1;                        // ext[0..48] carry, ext[49..368] tile
+    float2 *obuf = ext + NTAPS;
+    constexpr int NV = VEC ? FIR10_R / 2 : FIR10_R;         // loads per lane and tile
+    for (long s = (long) blockIdx.x * FIR10_WARPS + warp; s < n_streams; s += (long) gridDim.x * FIR10_WARPS) {
+        float2 *mem = memory + s * NTAPS;
+        float2 *x = sample + s * sample_stride;
+        __syncwarp();
+        for (int i = lane; i < NTAPS; i += 32) ext[i] = mem[i];
+        float4 nxt[NV];                                     // VEC: two samples; else .x/.y only
+        auto fetch = [&](int t0) {
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                nxt[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (VEC) {
+                    const int j = t0 + 2 * (lane + 32 * k);
+                    if (j + 1 < length) nxt[k] = *reinterpret_cast<const float4 *>(x + j);
+                    else if (j < length) {
+                        const float2 v = x[j];
+                        nxt[k] = make_float4(v.x, v.y, 0.f, 0.f);
+                    }
+                } else {
+                    const int j = t0 + lane + 32 * k;
+                    if (j < length) {
+                        const float2 v = x[j];
+                        nxt[k] = make_float4(v.x, v.y, 0.f, 0.f);
+                    }
+                }
+            }
+        };
+        fetch(0);
+        for (int t0 = 0; t0 < length; t0 += FIR10_TILE) {
+            const int n = min(FIR10_TILE, length - t0);
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                if (VEC) *reinterpret_cast<float4 *>(obuf + 2 * (lane + 32 * k)) = nxt[k];
+                else obuf[lane + 32 * k] = make_float2(nxt[k].x, nxt[k].y);
+            }
+            __syncwarp();
+            fetch(t0 + FIR10_TILE);                             // the next tile's loads fly during the math
+            u64 acc[FIR10_R];
+#pragma unroll
+            for (int r = 0; r < FIR10_R; r++) acc[r] = 0ull;
+            {
+                // output r of the lane is sum_k ext[10 lane + r + 1 + k] * c[k]: window ext[10 lane + 1 ..] = buf[10 lane + 2 ..]
+                const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(buf_all[warp] + FIR10_R * lane + 2);
+#pragma unroll
+                for (int jj = 0; jj < (NTAPS + FIR10_R - 1) / 2; jj++) {           // 29 x 128-bit = 58 samples
+                    const ulonglong2 v2 = wp[jj];
+#pragma unroll
+                    for (int half = 0; half < 2; half++) {
+                        const int j = 2 * jj + half;
+                        const u64 v = half ? v2.y : v2.x;
+#pragma unroll
+                        for (int r = 0; r < FIR10_R; r++) {
+                            const int k = j - r;
+                            if (k >= 0 && k < NTAPS) {
+                                // tolerance mode: the output gain is folded into the taps (one rounding fewer)
+                                if (FAST) acc[r] = pk_fma_bcast(v, tap<WIDE>(k) * FIR_GAIN, acc[r]);
+                                else acc[r] = pk_add(acc[r], pk_mul_bcast_pz(v, tap<WIDE>(k)));
+                            }
+                        }
+                    }
+                }
+            }
+            float2 c0 = ext[n + lane], c1 = make_float2(0.f, 0.f);
+            if (lane + 32 < NTAPS) c1 = ext[n + lane + 32];
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < FIR10_R; r += 2) {
+                float ar, ai, br, bi;
+                unpk(acc[r], ar, ai);
+                unpk(acc[r + 1], br, bi);
+                if (FAST)
+                    *reinterpret_cast<float4 *>(obuf + FIR10_R * lane + r) = make_float4(ar, ai, br, bi);
+                else
+                    *reinterpret_cast<float4 *>(obuf + FIR10_R * lane + r) =
+                        make_float4(__fmul_rn(ar, FIR_GAIN), __fmul_rn(ai, FIR_GAIN), __fmul_rn(br, FIR_GAIN), __fmul_rn(bi, FIR_GAIN));
+            }
+            ext[lane] = c0;
+            if (lane + 32 < NTAPS) ext[lane + 32] = c1;
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                if (VEC) {
+                    const int j = 2 * (lane + 32 * k);
+                    if (j + 1 < n) *reinterpret_cast<float4 *>(x + t0 + j) = *reinterpret_cast<const float4 *>(obuf + j);
+                    else if (j < n) x[t0 + j] = obuf[j];
+                } else {
+                    const int j = lane + 32 * k;
+                    if (j < n) x[t0 + j] = obuf[j];
+                }
+            }
+        }
+        __syncwarp();
         for (int i = lane; i < NTAPS; i += 32) mem[i] = ext[i];
     }
 }
 
 cudaError_t launch_fir_batch(bool wide, long n_streams, float2 *memory, float2 *sample, long sample_stride,
                              int length, cudaStream_t st, bool fast) {
-    const int grid = (int) std::min<long>((n_streams + FIR_WARPS - 1) / FIR_WARPS, 148L * 4);
-    const int thr = FIR_WARPS * 32;
-    if (fast) {
-        if (wide) fir_batch_kernel<true, true><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams);
-        else fir_batch_kernel<false, true><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams);
-    } else if (wide) fir_batch_kernel<true, false><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams);
-    else fir_batch_kernel<false, false><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams);
+    static const bool use_r5 = getenv("SC_FIR_R5") != nullptr;        // the 5-outputs-per-lane kernel, for comparison
+    if (use_r5) {
+        const int grid = (int) std::min<long>((n_streams + FIR_WARPS - 1) / FIR_WARPS, 148L * 4);
+        const int thr = FIR_WARPS * 32;
+        if (fast) {
+            if (wide) fir_batch_kernel<true, true><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams);
+            else fir_batch_kernel<false, true><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams);
+        } else if (wide) fir_batch_kernel<true, false><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams);
+        else fir_batch_kernel<false, false><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams);
+    } else {
+        const int grid = (int) std::min<long>((n_streams + FIR10_WARPS - 1) / FIR10_WARPS, 148L * 6);
+        const int thr = FIR10_WARPS * 32;
+        const bool vec = (((uintptr_t) sample) & 15) == 0 && (sample_stride & 1) == 0;
+#define SC_FIR_LAUNCH(W, F, V) fir_batch10_kernel<W, F, V><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams)
+        if (wide) {
+            if (fast) { if (vec) SC_FIR_LAUNCH(true, true, true); else SC_FIR_LAUNCH(true, true, false); }
+            else { if (vec) SC_FIR_LAUNCH(true, false, true); else SC_FIR_LAUNCH(true, false, false); }
+        } else {
+            if (fast) { if (vec) SC_FIR_LAUNCH(false, true, true); else SC_FIR_LAUNCH(false, true, false); }
+            else { if (vec) SC_FIR_LAUNCH(false, false, true); else SC_FIR_LAUNCH(false, false, false); }
+        }
+#undef SC_FIR_LAUNCH
+    }
     g_launch_count++;
     return cudaGetLastError();
 }
