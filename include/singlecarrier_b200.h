@@ -42,6 +42,8 @@ extern "C" {
 
 #define SC_FLAG_WIDE      0x1u      /* firwide=true: alpha=0.5 taps (qpsk.c:60)              */
 #define SC_FLAG_DEBUG_EQ  0x2u      /* keep eq_coeff[5] of every call (parity tests)         */
+#define SC_FLAG_PACKET    0x4u      /* packet mode (extension, see sc_rx_packets_*): TX scrambles,
+                                       RX can decode all 8 x 31 data symbols of a packet     */
 
 typedef struct sc_modem sc_modem;
 
@@ -133,6 +135,40 @@ int sc_rx_frames_dev(sc_modem *m, const int16_t *in, int64_t stream_stride, int 
                      sc_frame_result *results, int64_t result_stride, float *eq_dbg, void *stream);
 int sc_rx_frames_host(sc_modem *m, const int16_t *in, int64_t stream_stride, int n_frames,
                       sc_frame_result *results, int64_t result_stride, float *eq_dbg);
+
+/* ---- packet mode: an EXTENSION with no counterpart in the reference ----------------------------- */
+
+/*
+ * The reference decodes 31 of a packet's 8 x 31 data symbols, never scrambles on transmit and reads the late
+ * symbols of a window from unfiltered samples (qpsk.c:206-215, 386, 397, 161 -- TODOs / commented out).  With
+ * SC_FLAG_PACKET the library finishes them WITHOUT changing anything the reference computes: sc_rx_packets_*
+ * produce exactly the results of sc_rx_frames_* and, in addition, one sc_packet_result per VALID call n >= 2:
+ * kalman_reset, the 128 training steps, then data_eq over all 248 data symbols of the packet (equalizer state
+ * carried through the 8 frames, descrambler seeded per packet), on symbols taken from the CONTINUOUS
+ * matched-filter output at 1880 (n-2) + 5 (max_index + j) + T.  Specification: oracle/sc_oracle_ext.c.
+ * The transmit side (sc_tx_*_dev of a SC_FLAG_PACKET bank) seeds the TX register after every preamble and
+ * scrambles every data dibit (qpsk.c:386,397 un-commented); `bits` / `bits_out` are the payload.
+ */
+typedef struct {
+    uint64_t bits[8];       /* frame f: bit 2i = Q, bit 2i+1 = I of data symbol i, descrambled */
+    int32_t  stream;
+    uint32_t call_index;    /* the valid call this packet belongs to */
+    int16_t  max_index;
+    int16_t  matches;       /* of the packet's own training pass (equals the call's) */
+    float    cost;          /* sum of the 248 data_eq() returns */
+    uint32_t reserved0, reserved1;
+    uint64_t reserved2;
+} sc_packet_result;         /* 96 bytes */
+
+/* packets: capacity records, appended in no particular order; *n_packets receives the number of packets found
+ * (it can exceed capacity: the surplus is dropped).  _dev: device pointers, n_packets a device uint64 that is
+ * ACCUMULATED into; _host: host pointers, *n_packets is set. */
+int sc_rx_packets_dev(sc_modem *m, const int16_t *in, int64_t stream_stride, int n_frames,
+                      sc_frame_result *results, int64_t result_stride, sc_packet_result *packets,
+                      int64_t capacity, uint64_t *n_packets, void *stream);
+int sc_rx_packets_host(sc_modem *m, const int16_t *in, int64_t stream_stride, int n_frames,
+                       sc_frame_result *results, int64_t result_stride, sc_packet_result *packets,
+                       int64_t capacity, uint64_t *n_packets);
 
 /* Host helper: unpack results into the reference's on-disk format (qpsk.c:455-457): for every
  * VALID call, 62 bytes (0/1) are written to rows + (s*n_frames + j)*62; other rows untouched. */

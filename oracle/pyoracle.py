@@ -152,6 +152,40 @@ class Oracle:
         return out[0]
 
 
+EXT_PACKET_DTYPE = np.dtype([("call", "<i4"), ("max_index", "<i4"), ("matches", "<i4"), ("timing", "<i4"),
+                             ("cost", "<f4"), ("bits", "u1", (496,))])
+
+
+def ext_run_stream(oracle, samples: np.ndarray, max_packets: int = 64, wide: bool = False, foffset: float = 0.0):
+    """Packet-mode extension (oracle/sc_oracle_ext.c, NO reference counterpart): the ordinary receiver plus the
+    full 8 x 31 symbol decode of every valid call.  Returns (bits[nf,62], stats[nf], packets[EXT_PACKET_DTYPE])."""
+    L = oracle.lib
+    L.sco_ext_run_stream.restype = C.c_int
+    L.sco_ext_run_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.sco_ext_sizeof_packet.restype = C.c_ulong
+    assert int(L.sco_ext_sizeof_packet()) == EXT_PACKET_DTYPE.itemsize
+    x = np.ascontiguousarray(samples, dtype="<i2")
+    nf = x.size // FRAME_SIZE
+    bits = np.full((nf, BITS_PER_CALL), 255, np.uint8)
+    stats = np.zeros(nf, STATS_DTYPE)
+    pk = np.zeros(max_packets, EXT_PACKET_DTYPE)
+    n = L.sco_ext_run_stream(_p(x), nf, int(wide), float(foffset), _p(bits), _p(stats), _p(pk), max_packets)
+    return bits, stats, pk[:n]
+
+
+def ext_tx_packet(oracle, state, bits: np.ndarray) -> np.ndarray:
+    """One packet with TX scrambling enabled (qpsk.c:386,397 un-commented): 1880 int16 samples."""
+    L = oracle.lib
+    L.sco_ext_tx_packet.restype = C.c_int
+    L.sco_ext_tx_packet.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    b = np.ascontiguousarray(bits, np.uint8)
+    assert b.size == 496
+    out = np.zeros(FRAME_SIZE, "<i2")
+    n = L.sco_ext_tx_packet(_p(state), _p(out), _p(b))
+    assert n == FRAME_SIZE
+    return out
+
+
 def synth_streams(oracle, rng, n_streams, n_frames, noise_levels=(0.0, 30.0, 300.0, 1500.0, 4000.0),
                   max_lead=2000, gaps=(903, 0, 500, 1880)):
     """Oracle-TX loop-back streams with random lead-in, dead air and additive noise -> int16[n, n_frames*1880]."""

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsinglecarrier_b200.so")
 
 SC_OK, SC_EINVAL, SC_ECUDA, SC_ENOMEM, SC_ESTATE = 0, -1, -2, -3, -4
-SC_FLAG_WIDE, SC_FLAG_DEBUG_EQ = 0x1, 0x2
+SC_FLAG_WIDE, SC_FLAG_DEBUG_EQ, SC_FLAG_PACKET = 0x1, 0x2, 0x4
 
 
 class SingleCarrierError(RuntimeError):
@@ -55,6 +55,8 @@ def _load() -> C.CDLL:
     sig("sc_profile_read", i32, vp, C.POINTER(C.c_double))
     sig("sc_rx_frames_dev", i32, vp, vp, i64, i32, vp, i64, vp, vp)
     sig("sc_rx_frames_host", i32, vp, vp, i64, i32, vp, i64, vp)
+    sig("sc_rx_packets_dev", i32, vp, vp, i64, i32, vp, i64, vp, i64, vp, vp)
+    sig("sc_rx_packets_host", i32, vp, vp, i64, i32, vp, i64, vp, i64, C.POINTER(C.c_uint64))
     sig("sc_unpack_bits", None, vp, i64, vp)
     sig("sc_tx_packets_dev", i32, vp, vp, vp, u64, i32, i32, vp, vp, i64, i64, vp)
     sig("sc_tx_channel_dev", i32, vp, vp, vp, u64, i32, i32, vp, C.POINTER(Channel), vp, i64, i64, vp)

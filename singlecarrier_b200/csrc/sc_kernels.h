@@ -63,6 +63,29 @@ cudaError_t launch_ber_stats(const sc_frame_result *results, long n_streams, lon
                              const uint8_t *tx_bits, int n_packets, const int *lead_in, int gap, const int *group,
                              int n_groups, unsigned long long *counters, cudaStream_t st);
 
+// sc_packet_kernels.cu -- packet mode (extension)
+constexpr int PK_DATA = 8 * SC_DATA_SYMBOLS;                              // 248 data symbols per packet
+constexpr int PK_SYMS = SC_PREAMBLE_LENGTH + PK_DATA + SC_EQ_LENGTH - 1;  // 380 symbols feed one packet decode
+struct PacketKey {
+    unsigned long long k[8];    // scrambler keystream of the 8 data frames, register seeded per packet
+};
+struct PacketSrc {              // one block of calls [call0, call0 + nf) of a slab of streams
+    const sc_frame_result *results;
+    long result_stride;
+    const int16_t *in;          // block frames, stream s at in + s * stride
+    long stride;
+    const int16_t *hist1, *hist2;       // frames call0-1 and call0-2, [stream][1880]
+    const float2 *mix0;         // phasor table of frame call0-1; frames call0.. follow
+    const float2 *mix_hist2;    // phasor table of frame call0-2
+    const int *timing_before_call0, *timing_at_call0;   // rx_timing at entry of calls call0-1 and call0
+    uint32_t call0;
+    int stream0;                // bank index of the slab's first stream
+    bool wide;
+};
+cudaError_t launch_packet_pass(const PacketSrc &src, int n_streams, int j_lo, int j_hi, int cap, int2 *list, int *count,
+                               float2 *sym, const PacketKey &key, sc_packet_result *packets, long packet_capacity,
+                               unsigned long long *n_packets, cudaStream_t st);
+
 // sc_tx_kernels.cu
 struct TxArgs {
     const uint8_t *bits;        // [n][n_packets][8][62] or nullptr
@@ -78,6 +101,8 @@ struct TxArgs {
     long n_streams;
     bool wide;
     bool use_channel;
+    bool scramble;              // packet mode: data bits go through scramble(tx), register seeded per packet
+    PacketKey key;
     sc_channel ch;
 };
 cudaError_t launch_tx(const TxArgs &a, cudaStream_t st);

@@ -51,7 +51,8 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {   //
 
 // ---- data bits: pack the caller's bits, or draw them, one 62-bit word per (stream, packet, frame)
 __global__ void tx_bits_kernel(const uint8_t *__restrict__ bits, uint8_t *__restrict__ bits_out,
-                               unsigned long long *__restrict__ words, unsigned long long seed, long n_words) {
+                               unsigned long long *__restrict__ words, unsigned long long seed, long n_words,
+                               bool scramble, PacketKey key) {
     const long w = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_words) return;
     unsigned long long v = 0;
@@ -61,7 +62,9 @@ __global__ void tx_bits_kernel(const uint8_t *__restrict__ bits, uint8_t *__rest
     } else {
         v = mix64(seed ^ mix64((unsigned long long) w)) & ((1ull << SC_BITS_PER_CALL) - 1ull);
     }
-    words[w] = v;
+    // packet mode (extension): scramble(&sdata, tx) with the register seeded after each preamble, qpsk.c:386,397;
+    // w % 8 is the data frame inside the packet.  bits_out stays the payload.
+    words[w] = scramble ? v ^ key.k[w & 7] : v;
     if (bits_out != nullptr) {
         uint8_t *b = bits_out + w * SC_BITS_PER_CALL;
         for (int j = 0; j < SC_BITS_PER_CALL; j++) b[j] = (uint8_t) ((v >> j) & 1ull);
@@ -183,7 +186,8 @@ cudaError_t launch_tx(const TxArgs &a, cudaStream_t st) {
     e = cudaMallocAsync((void **) &words, (size_t) std::max<long>(n_words, 1) * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     if (n_words > 0) {
-        tx_bits_kernel<<<(unsigned) ((n_words + 255) / 256), 256, 0, st>>>(a.bits, a.bits_out, words, a.seed, n_words);
+        tx_bits_kernel<<<(unsigned) ((n_words + 255) / 256), 256, 0, st>>>(a.bits, a.bits_out, words, a.seed, n_words,
+                                                                            a.scramble, a.key);
         g_launch_count++;
     }
     TxGeom g;

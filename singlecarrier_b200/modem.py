@@ -12,7 +12,7 @@ from typing import Optional
 
 import numpy as np
 
-from ._lib import SC_FLAG_DEBUG_EQ, SC_FLAG_WIDE, Channel, check, lib
+from ._lib import SC_FLAG_DEBUG_EQ, SC_FLAG_PACKET, SC_FLAG_WIDE, Channel, check, lib
 
 FRAME_SIZE = 1880
 SYMBOLS_PER_FRAME = 376
@@ -28,6 +28,11 @@ RESULT_DTYPE = np.dtype([("bits", "<u8"), ("max_value", "<f4"), ("cost", "<f4"),
                          ("matches", "<i2"), ("rx_timing", "<i2"), ("valid", "u1"), ("reserved0", "u1"),
                          ("call_index", "<u4"), ("reserved1", "<u4")])
 assert RESULT_DTYPE.itemsize == 32
+# sc_packet_result (packet mode, an extension without a counterpart in the reference)
+PACKET_DTYPE = np.dtype([("bits", "<u8", (8,)), ("stream", "<i4"), ("call_index", "<u4"), ("max_index", "<i2"),
+                         ("matches", "<i2"), ("cost", "<f4"), ("reserved0", "<u4"), ("reserved1", "<u4"),
+                         ("reserved2", "<u8")])
+assert PACKET_DTYPE.itemsize == 96
 
 
 def keystream_word(call_index: int) -> int:
@@ -36,6 +41,12 @@ def keystream_word(call_index: int) -> int:
 
 def launch_count() -> int:
     return int(lib.sc_launch_count())
+
+
+def unpack_packet_bits(packets: np.ndarray) -> np.ndarray:
+    """PACKET_DTYPE records -> payload bits [n, 8, 62] (bit-per-byte, the layout of sc_tx_*_dev's bits_out)."""
+    w = packets["bits"].astype(np.uint64)                                       # [n, 8]
+    return ((w[:, :, None] >> np.arange(62, dtype=np.uint64)[None, None, :]) & np.uint64(1)).astype(np.uint8)
 
 
 def unpack_bits(results: np.ndarray, rows: Optional[np.ndarray] = None) -> np.ndarray:
@@ -136,9 +147,10 @@ class ModemBank:
     """A bank of ``n_streams`` synchronized modems on one GPU (sc_modem handle)."""
 
     def __init__(self, n_streams: int, device: int = 0, wide: bool = False, foffset_hz: float = 0.0,
-                 debug_eq: bool = False):
+                 debug_eq: bool = False, packet: bool = False):
         self._h = C.c_void_p()
-        flags = (SC_FLAG_WIDE if wide else 0) | (SC_FLAG_DEBUG_EQ if debug_eq else 0)
+        flags = (SC_FLAG_WIDE if wide else 0) | (SC_FLAG_DEBUG_EQ if debug_eq else 0) | (SC_FLAG_PACKET if packet else 0)
+        self.packet = packet
         check(lib.sc_create(C.byref(self._h), device, n_streams, flags, foffset_hz))
         self.n_streams = n_streams
         self.device = device
@@ -219,6 +231,30 @@ class ModemBank:
         check(lib.sc_rx_frames_host(self._h, samples.ctypes.data, stride, n_frames, results.ctypes.data,
                                     results.strides[0] // 32, _ptr(eq)))
         return results, eq
+
+    def rx_packets_host(self, samples: np.ndarray, n_frames: Optional[int] = None, capacity: Optional[int] = None):
+        """Packet mode (extension): the ordinary results plus one PACKET_DTYPE record per valid call n >= 2 with all
+        8 x 62 bits of the packet, sorted by (stream, call).  Returns (results, packets, n_found)."""
+        assert samples.dtype == np.int16 and samples.ndim == 2 and samples.shape[0] == self.n_streams
+        stride = samples.strides[0] // 2
+        if n_frames is None:
+            n_frames = samples.shape[1] // FRAME_SIZE
+        results = np.zeros((self.n_streams, n_frames), RESULT_DTYPE)
+        if capacity is None:
+            capacity = self.n_streams * n_frames
+        packets = np.zeros(max(capacity, 1), PACKET_DTYPE)
+        n = C.c_uint64(0)
+        check(lib.sc_rx_packets_host(self._h, samples.ctypes.data, stride, n_frames, results.ctypes.data,
+                                     results.strides[0] // 32, packets.ctypes.data, capacity, C.byref(n)))
+        got = packets[: min(int(n.value), capacity)]
+        got = got[np.lexsort((got["call_index"], got["stream"]))]
+        return results, got, int(n.value)
+
+    def rx_packets_dev(self, samples, n_frames: int, results, packets, n_packets, stream: int = 0) -> None:
+        """Device form: packets = CUDA uint8 [capacity * 96], n_packets = CUDA int64[1] (accumulated into)."""
+        check(lib.sc_rx_packets_dev(self._h, samples.data_ptr(), samples.stride(0), n_frames, results.data_ptr(),
+                                    results.stride(0) // 32, packets.data_ptr(), packets.numel() // 96,
+                                    n_packets.data_ptr(), stream))
 
     def rx_frames_dev(self, samples, n_frames: int, results, eq_dbg=None, stream: int = 0) -> None:
         """samples: CUDA int16 tensor [n_streams, stride]; results: CUDA uint8 tensor
