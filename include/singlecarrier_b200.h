@@ -232,10 +232,16 @@ int sc_fir_batch_dev(int device, int64_t n_streams, int wide, float *memory, flo
  *   sc_preamble_search_batch_dev         all 128 correlations are PROPOSED on the tensor cores (bf16 split of the
  *                                        operands, fp32 accumulation, rigorous error bound), then only the lags that
  *                                        can be the maximum are evaluated with the reference's exact sequential sums;
+ *   sc_preamble_search_fft_batch_dev     the same scheme with an FFT proposer: two 256-point transforms held in the
+ *                                        registers of one warp (radix-4 butterflies, lane exchanges by warp shuffle),
+ *                                        warp-reduced argmax, exact verification of the candidates;
  *   sc_preamble_search_direct_batch_dev  every lag with the exact sums (the form the RX chain fuses). */
 int sc_preamble_search_batch_dev(int device, int64_t n_streams, const float *symbols,
                                  int64_t symbol_stride, int32_t *max_index, float *max_value,
                                  void *stream);
+int sc_preamble_search_fft_batch_dev(int device, int64_t n_streams, const float *symbols,
+                                     int64_t symbol_stride, int32_t *max_index, float *max_value,
+                                     void *stream);
 int sc_preamble_search_direct_batch_dev(int device, int64_t n_streams, const float *symbols,
                                         int64_t symbol_stride, int32_t *max_index, float *max_value,
                                         void *stream);

@@ -33,6 +33,9 @@ cudaError_t launch_search_batch(long n_streams, const float2 *symbols, long symb
 void search_mma_make_table(uint32_t *table /* [9][32][4] */);
 cudaError_t launch_search_mma_batch(long n_streams, const float2 *symbols, long symbol_stride, const void *a_table,
                                     int *max_index, float *max_value, cudaStream_t st);
+void search_fft_make_table(float *table /* [8][32][2] */);
+cudaError_t launch_search_fft_batch(long n_streams, const float2 *symbols, long symbol_stride, const float2 *tw,
+                                    const void *ptab, int *max_index, float *max_value, cudaStream_t st);
 cudaError_t launch_track_window_batch(long n_streams, const float2 *symbols, long symbol_stride,
                                       const int *max_index, const float *max_value, int *rx_timing,
                                       uint32_t call_index, unsigned long long keystream,

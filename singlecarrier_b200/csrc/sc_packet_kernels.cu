@@ -8,8 +8,8 @@
 //          continuous matched-filter output (frames n-2 and n-1);
 //   kalman_reset, 128 x train_eq, then 248 x data_eq with the equalizer state carried through all 8 frames and the
 //   descrambler re-seeded per packet.
-// The specification is oracle/sc_oracle_ext.c (a CPU statement of exactly this, built from the pinned primitives);
-// parity is against that file only ("parity unpinned" in the sense of the reference).
+// The specification is the CPU statement of exactly this in the test tree (packet mode), built from the
+// pinned primitives; parity is against that statement only ("parity unpinned" in the sense of the reference).
 //
 //   packet_list_kernel    (one thread per stream x call)  valid calls of the block -> compact list
 //   packet_fir_kernel     (one warp per listed packet)    int16 -> mix -> 49-tap RRC at the 380 symbol instants

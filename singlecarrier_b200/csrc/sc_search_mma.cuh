@@ -147,6 +147,46 @@ __device__ __forceinline__ void search_warp_unpadded(const float *__restrict__ D
     if (!(best_val > 0.0f)) best_idx = 0;
 }
 
+// Exact verification by one 16-lane half of a warp: lane pair (2k, 2k+1) of the half evaluates the reference's sums
+// (re, im) of candidate k (up to SM_MAX_CAND), then the reference's argmax rule -- strict '>' scanning the lags
+// upwards, initial maximum 0.0f -- is applied to the exact values.  n_cand > SM_MAX_CAND gives (0, -1): the caller
+// falls back to the full exact search.  All 32 lanes call; result in every lane of the half.
+__device__ __forceinline__ void search_verify16(const float *__restrict__ D, const float *__restrict__ E,
+                                                const int *__restrict__ cand, int nc, int lane, int &ei, float &ev) {
+    const int vk = (lane & 15) >> 1, vc = lane & 1;
+    const bool have = vk < nc && nc <= SM_MAX_CAND;
+    const int L = have ? cand[vk] : 0;
+    const float part = search_exact_sum(vc ? E : D, L);
+    const float sq = __fmul_rn(part, part);
+    // cnormf: re*re + im*im (qpsk.c:75-80); a float add commutes, so both lanes of the pair get the same bits
+    ev = __fadd_rn(sq, __shfl_xor_sync(0xffffffffu, sq, 1));
+    ei = L;
+    if (!have) {
+        ev = -1.0f;
+        ei = 1 << 20;
+    }
+    // largest exact value, smallest lag among equals == strict '>' scanning lags upwards
+#pragma unroll
+    for (int off = 2; off < 16; off <<= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, ev, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, ei, off);
+        if (ov > ev || (ov == ev && oi < ei)) {
+            ev = ov;
+            ei = oi;
+        }
+    }
+    if (!(ev > 0.0f)) ei = 0, ev = fmaxf(ev, 0.0f);
+}
+
+// Error bound -> candidate threshold.  |approx - reference| <= delta per component, so
+// |v_approx - v_ref| <= mu = 2 delta (m + delta) + 2^-20 v_max with m = sqrt(2 v_max) >= |re| + |im| of every lag,
+// and every lag whose approximate value reaches v_max - 2 mu may be the true maximum.
+__device__ __forceinline__ float search_candidate_threshold(float vmax, float delta) {
+    const float m = __fmul_rn(sqrtf(__fmul_rn(2.0f, vmax)), 1.0001f);
+    const float mu = __fadd_rn(__fmul_rn(__fmul_rn(2.0f, delta), __fadd_rn(m, delta)), __fmul_rn(vmax, 0x1p-20f));
+    return __fsub_rn(vmax, __fmul_rn(mu, 2.002f));
+}
+
 // Proposer + verifier for the TWO windows staged in sm (window 1 may be all zeros).  All 32 lanes call.
 // s_abs[w] = sum(|d|+|e|) of window w (any lane's copy after a warp reduction).  Results in every lane.
 __device__ __forceinline__ void search_mma_pair(SearchMmaSmem &sm, const uint4 *__restrict__ a_table, int lane,
@@ -198,10 +238,7 @@ __device__ __forceinline__ void search_mma_pair(SearchMmaSmem &sm, const uint4 *
         }
     }
     // ---- bound and candidates
-    const float delta = __fmul_rn(s_abs[w], 0x1.004p-13f);
-    const float m = __fmul_rn(sqrtf(__fmul_rn(2.0f, vmax)), 1.0001f);
-    const float mu = __fadd_rn(__fmul_rn(__fmul_rn(2.0f, delta), __fadd_rn(m, delta)), __fmul_rn(vmax, 0x1p-20f));
-    const float thr = __fsub_rn(vmax, __fmul_rn(mu, 2.002f));
+    const float thr = search_candidate_threshold(vmax, __fmul_rn(s_abs[w], 0x1.004p-13f));
     if (lane < 2) sm.n_cand[lane] = 0;
     __syncwarp();
     if ((tid & 1) == 0) {
@@ -214,31 +251,11 @@ __device__ __forceinline__ void search_mma_pair(SearchMmaSmem &sm, const uint4 *
         }
     }
     __syncwarp();
-    // ---- verify: lanes 0..15 take window 0, 16..31 window 1; lane pair (2k, 2k+1) = (re, im) of candidate k
-    const int vw = lane >> 4, vk = (lane & 15) >> 1, vc = lane & 1;
-    const int nc = sm.n_cand[vw];
-    const bool have = vk < nc && nc <= SM_MAX_CAND;
-    const int L = have ? sm.cand[vw][vk] : 0;
-    const float part = search_exact_sum(sm.de[vw][vc], L);
-    const float sq = __fmul_rn(part, part);
-    // cnormf: re*re + im*im (qpsk.c:75-80); a float add commutes, so both lanes of the pair get the same bits
-    float ev = __fadd_rn(sq, __shfl_xor_sync(0xffffffffu, sq, 1));
-    int ei = L;
-    if (!have) {
-        ev = -1.0f;
-        ei = 1 << 20;
-    }
-    // largest exact value, smallest lag among equals == strict '>' scanning lags upwards
-#pragma unroll
-    for (int off = 2; off < 16; off <<= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, ev, off);
-        const int oi = __shfl_xor_sync(0xffffffffu, ei, off);
-        if (ov > ev || (ov == ev && oi < ei)) {
-            ev = ov;
-            ei = oi;
-        }
-    }
-    if (!(ev > 0.0f)) ei = 0, ev = fmaxf(ev, 0.0f);
+    // ---- verify: lanes 0..15 take window 0, 16..31 window 1
+    const int vw = lane >> 4;
+    float ev;
+    int ei;
+    search_verify16(sm.de[vw][0], sm.de[vw][1], sm.cand[vw], sm.n_cand[vw], lane, ei, ev);
     // publish window results to every lane
 #pragma unroll
     for (int ww = 0; ww < 2; ww++) {

@@ -8,9 +8,11 @@
 #include "sc_tracker.cuh"
 #include "sc_search.cuh"
 #include "sc_search_mma.cuh"
+#include "sc_fft256.cuh"
 #include "sc_track_core.cuh"
 #include "sc_kernels.h"
 
+#include <math.h>
 #include <stdlib.h>
 
 namespace sc {
@@ -337,6 +339,132 @@ search_mma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride, 
             max_value[2 * pr + lane] = lane ? bv[1] : bv[0];
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same search with an FFT proposer (BASELINE.json north star: "preamble correlation ... as a hand-written
+// batched FFT with warp-shuffle butterflies ... plus a warp-reduced argmax"): one warp per window, the 256-point
+// transforms stay in registers (sc_fft256.cuh).
+//   c[L] = sum_i pre[i] s[L+i]  <=>  C[k] = S[k] * Pt[k],  Pt[k] = sum_i pre[i] e^{+2 pi j k i / 256}
+//   S = FFT(s) (255 symbols, zero padded), C = S .* Pt / 256, c = IFFT(C) = conj(FFT(conj C))
+// The two transforms use different register layouts (natural order in, digit-permuted out), so conj(C) goes
+// through shared memory once.  Lags 0..127 are the registers {0, 1, 4, 5} of every lane.  Error of the float32
+// transforms is bounded by delta = 2^-12 * sum(|d| + |e|) per component (8 radix-4 stages, |Pt| <= 182); the
+// candidates are verified exactly as in the tensor-core variant, so the result is the reference's, bit for bit.
+// ------------------------------------------------------------------------------------------------
+constexpr int SFFT_WARPS = 4;
+
+struct SearchFftSmem {
+    float de[2][SM_DE_FLOATS];          // d[256], e[256] (+8 words: 8 banks apart)
+    float2 xpose[256];
+    int cand[SM_MAX_CAND];
+    int n_cand;
+};
+
+__global__ void __launch_bounds__(SFFT_WARPS * 32)
+search_fft_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride, const c32 *__restrict__ tw,
+                        const float2 *__restrict__ ptab, int *__restrict__ max_index, float *__restrict__ max_value,
+                        long n_streams) {
+    __shared__ __align__(16) SearchFftSmem sm_all[SFFT_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    SearchFftSmem &sm = sm_all[warp];
+    Fft256Twiddles T;
+    T.load(tw, lane);
+    c32 pt[8];                                              // Pt / 256 in the transform's output layout
+#pragma unroll
+    for (int r = 0; r < 8; r++) pt[r] = from2(__ldg(ptab + r * 32 + lane));
+    for (long s = (long) blockIdx.x * SFFT_WARPS + warp; s < n_streams; s += (long) gridDim.x * SFFT_WARPS) {
+        const float2 *x = symbols + s * symbol_stride;
+        c32 v[8];
+        float part = 0.0f;
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int xx = lane + 32 * r;
+            const float2 sv = xx < SEARCH_SYMS ? x[xx] : make_float2(0.0f, 0.0f);
+            v[r] = from2(sv);
+            const float d = __fsub_rn(sv.x, sv.y), e = __fadd_rn(sv.y, sv.x);      // qpsk.c:88-96 with pre = v(1+i)
+            sm.de[0][xx] = d;
+            sm.de[1][xx] = e;
+            part = __fadd_rn(part, __fadd_rn(fabsf(d), fabsf(e)));
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, off));
+        // ---- propose
+        fft256_regs<false>(v, lane, T);
+#pragma unroll
+        for (int r = 0; r < 8; r++) sm.xpose[fft256_out_index(lane, r)] = to2(cconj(cmul(v[r], pt[r])));
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[r] = from2(sm.xpose[lane + 32 * r]);
+        fft256_regs<false>(v, lane, T);
+        float val[4], vmax = 0.0f;
+        int imax = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int r = (q & 1) + 4 * (q >> 1);                                   // registers 0, 1, 4, 5: lags < 128
+            val[q] = __fadd_rn(__fmul_rn(v[r].r, v[r].r), __fmul_rn(v[r].i, v[r].i));
+            if (val[q] > vmax) {
+                vmax = val[q];
+                imax = fft256_out_index(lane, r);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {                                    // warp-reduced argmax
+            const float ov = __shfl_xor_sync(0xffffffffu, vmax, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, imax, off);
+            if (ov > vmax || (ov == vmax && oi < imax)) {
+                vmax = ov;
+                imax = oi;
+            }
+        }
+        const float thr = search_candidate_threshold(vmax, __fmul_rn(part, 0x1.004p-12f));
+        if (lane == 0) sm.n_cand = 0;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (val[q] >= thr) {
+                const int pos = atomicAdd(&sm.n_cand, 1);
+                if (pos < SM_MAX_CAND) sm.cand[pos] = fft256_out_index(lane, (q & 1) + 4 * (q >> 1));
+            }
+        }
+        __syncwarp();
+        // ---- verify (both halves of the warp do the same work: only one window here)
+        int bi;
+        float bv;
+        search_verify16(sm.de[0], sm.de[1], sm.cand, sm.n_cand, lane, bi, bv);
+        if (sm.n_cand > SM_MAX_CAND) search_warp_unpadded(sm.de[0], sm.de[1], lane, bi, bv);
+        if (lane == 0) {
+            max_index[s] = bi;
+            max_value[s] = bv;
+        }
+    }
+}
+
+// Pt[k] / 256 in the output layout of fft256_regs (host side, double precision)
+void search_fft_make_table(float *table /* [8][32][2] */) {
+    for (int r = 0; r < 8; r++)
+        for (int lane = 0; lane < 32; lane++) {
+            const int k = fft256_out_index(lane, r);
+            double re = 0.0, im = 0.0;
+            for (int i = 0; i < PRE; i++) {
+                const double ph = 2.0 * M_PI * (double) ((k * i) & 255) / 256.0, v = (double) preamble_value(i);
+                // pre[i] = v (1 + j):  v (1 + j)(cos + j sin) = v (cos - sin) + j v (cos + sin)
+                re += v * (cos(ph) - sin(ph));
+                im += v * (cos(ph) + sin(ph));
+            }
+            table[(r * 32 + lane) * 2] = (float) (re / 256.0);
+            table[(r * 32 + lane) * 2 + 1] = (float) (im / 256.0);
+        }
+}
+
+cudaError_t launch_search_fft_batch(long n_streams, const float2 *symbols, long symbol_stride, const float2 *tw,
+                                    const void *ptab, int *max_index, float *max_value, cudaStream_t st) {
+    const int grid = (int) std::min<long>((n_streams + SFFT_WARPS - 1) / SFFT_WARPS, 148L * 4);
+    search_fft_batch_kernel<<<grid, SFFT_WARPS * 32, 0, st>>>(symbols, symbol_stride, reinterpret_cast<const c32 *>(tw),
+                                                              (const float2 *) ptab, max_index, max_value, n_streams);
+    g_launch_count++;
+    return cudaGetLastError();
 }
 
 // A fragments of the 9 Toeplitz tiles (sc_search_mma.cuh), host side

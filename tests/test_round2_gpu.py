@@ -269,7 +269,7 @@ def test_tensor_core_proposed_search_equals_direct_search(sc, oracle):
         sym[k + 350:k + 400, 77] = np.nextafter(sym[k + 400:k + 450, 77].real, np.float32(9)) + 1j * sym[k + 400:k + 450, 77].imag
         d = torch.from_numpy(sym.view(np.float32)).cuda()
         out = {}
-        for name in ("sc_preamble_search_batch_dev", "sc_preamble_search_direct_batch_dev"):
+        for name in ("sc_preamble_search_batch_dev", "sc_preamble_search_fft_batch_dev", "sc_preamble_search_direct_batch_dev"):
             idx = torch.full((ns,), -7, dtype=torch.int32, device="cuda")
             val = torch.full((ns,), -7.0, dtype=torch.float32, device="cuda")
             sc._lib.check(getattr(sc.lib, name)(0, ns, d.data_ptr(), stride, idx.data_ptr(), val.data_ptr(), 0))
@@ -278,6 +278,9 @@ def test_tensor_core_proposed_search_equals_direct_search(sc, oracle):
         (ai, av), (bi, bv) = out["sc_preamble_search_batch_dev"], out["sc_preamble_search_direct_batch_dev"]
         bad = np.nonzero((ai != bi) | (av.view(np.uint32) != bv.view(np.uint32)))[0]
         assert bad.size == 0, (bad[:10], ai[bad[:10]], bi[bad[:10]], av[bad[:10]], bv[bad[:10]])
+        fi, fv = out["sc_preamble_search_fft_batch_dev"]
+        bad = np.nonzero((fi != bi) | (fv.view(np.uint32) != bv.view(np.uint32)))[0]
+        assert bad.size == 0, ("fft proposer", bad[:10], fi[bad[:10]], bi[bad[:10]], fv[bad[:10]], bv[bad[:10]])
         assert (ai[:k] == np.arange(k) % 128)[np.arange(k) % 7 >= 2].mean() > 0.99       # strong preambles are found
         for s in list(range(0, 40)) + list(range(k, k + 150, 7)):                          # and both equal the oracle
             oi, ov = oracle.search(sym[s])

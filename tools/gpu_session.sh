@@ -1,14 +1,14 @@
 #!/bin/bash
 # Typical B200 session (run through gpurun): parity tests, benchmark, then the ncu captures that
-# tools/profile_summary.py turns into profiles/rNN_*.md.  Usage: bash tools/gpu_session.sh r01
+# tools/profile_summary.py turns into profiles/rNN_*.md / rNN_ncu_raw.csv.  Usage: bash tools/gpu_session.sh r02
 set -x
-R=${1:-r01}
+R=${1:-r02}
 mkdir -p gpurun_out
 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null > gpurun_out/bench_ref_$R.json
 python bench.py 2>gpurun_out/bench.err > gpurun_out/bench_$R.json
-python tools/stage_bench.py 2>&1 | tail -8 > gpurun_out/stage_bench_$R.md
+python tools/stage_bench.py 2>&1 | tail -10 > gpurun_out/stage_bench_$R.md
 # launch list (every launch with its device time; compare shares)
 CMD="python bench.py --streams 131072 --seconds 2 --steps 2 --warmup 3 --no-e2e --no-cpu"
 $CMD > gpurun_out/plain_$R.log 2>&1 &&
@@ -18,3 +18,7 @@ CMD2="python bench.py --streams 131072 --seconds 1 --steps 1 --warmup 3 --no-e2e
 $CMD2 > gpurun_out/plain2_$R.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'frontend_kernel|track_kernel' -s 10 -c 2 -o gpurun_out/prof_$R $CMD2 > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
+python bench.py --no-e2e --no-cpu 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); r=d['roofline']; o=r['other_kernel']
+print('value %.0f Msym/s  ms/step %.2f | %s %.3f | %s %.3f'%(d['value'],d['ms_per_step'],r['kernel'],r['ms_per_launch'],o['kernel'],o['ms_per_launch']))"

@@ -50,6 +50,9 @@ val = torch.empty(ns, dtype=torch.float32, device="cuda")
 ms = timeit(lambda: check(L.sc_preamble_search_batch_dev(0, ns, s.data_ptr(), 256, idx.data_ptr(), val.data_ptr(), None)))
 gbs = ns * 2048 / ms / 1e6
 rows.append(("search_mma_batch_kernel (tensor-core proposer + exact verifier)", f"{ns} windows", ms, gbs, gbs / peak, "-"))
+ms = timeit(lambda: check(L.sc_preamble_search_fft_batch_dev(0, ns, s.data_ptr(), 256, idx.data_ptr(), val.data_ptr(), None)))
+gbs = ns * 2048 / ms / 1e6
+rows.append(("search_fft_batch_kernel (warp-shuffle FFT proposer + exact verifier)", f"{ns} windows", ms, gbs, gbs / peak, "-"))
 ms = timeit(lambda: check(L.sc_preamble_search_direct_batch_dev(0, ns, s.data_ptr(), 256, idx.data_ptr(), val.data_ptr(), None)))
 gbs = ns * 2048 / ms / 1e6
 rows.append(("search_batch_kernel (every lag exact)", f"{ns} windows", ms, gbs, gbs / peak, f"{ns * 33152 / ms / 1e9:.1f} Tops/s of 37.2"))
