@@ -98,6 +98,10 @@ uint64_t sc_launch_count(void);
 #define SC_H2D_ROWS       1   /* per block of frames: one 2-D copy, rows trimmed by 256 samples                 */
 #define SC_H2D_FULL       2   /* whole frames: one 2-D copy per block, a plain 1-D copy when streams are dense  */
 #define SC_H2D_COLUMNS_3D 3   /* the COLUMNS bytes as one 3-D copy per block (stream_stride % 1880 == 0)        */
+/* SC_OPT_FE_SEARCH: how the fused front-end finds the preamble.  Identical results either way. */
+#define SC_OPT_FE_SEARCH     4
+#define SC_FE_SEARCH_DIRECT  0   /* all 128 lags with the exact sequential sums                                   */
+#define SC_FE_SEARCH_MMA     1   /* proposed on the tensor cores, the candidates verified with the exact sums      */
 int  sc_set_option(sc_modem *m, int option, int64_t value);
 int  sc_profile_read(sc_modem *m, double out[4]);
 /* bytes queued host->device (out[0]) and device->host (out[1]) by sc_rx_frames_host since sc_create */

@@ -18,7 +18,7 @@ cudaError_t launch_nco_table(float2 *phase_state, float2 rect, int pattern, int 
                              float2 *out, cudaStream_t st);
 cudaError_t launch_frontend(bool wide, const int16_t *in, long stream_stride, const float2 *mix_table,
                             const int *timing_cur, const int *timing_next, float2 *win, int *max_index,
-                            float *max_value, int n_streams, cudaStream_t st);
+                            float *max_value, int n_streams, cudaStream_t st, const void *search_a_table = nullptr);
 cudaError_t launch_track(bool debug_eq, const float2 *win, const int *max_index, const float *max_value,
                          const int *timing_cur, int *timing_next, sc_frame_result *results, long result_stride,
                          float *eq_dbg, float *state_dbg, uint32_t call_index, unsigned long long keystream,

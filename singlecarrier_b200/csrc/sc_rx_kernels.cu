@@ -12,6 +12,7 @@
 #include "sc_tables.cuh"
 #include "sc_tracker.cuh"
 #include "sc_search.cuh"
+#include "sc_search_mma.cuh"
 #include "sc_track_core.cuh"
 #include "sc_kernels.h"
 
@@ -70,7 +71,12 @@ constexpr int FE_FIR_LANES = 29;
 constexpr int FE_PASS_OUT = FE_FIR_LANES * FE_R;            // 145
 constexpr int FE_PASS_SAMP = NTAPS + CYC * (FE_PASS_OUT - 1);   // 769
 constexpr int FE_FRONT = 2;                                 // slack slots in front (pair alignment), +1 for parity
-constexpr int FE_BUF = 784;                                 // FE_FRONT + 1 + 769 + pair slack, rounded
+constexpr int FE_BUF = 840;                                 // >= FE_FRONT + 1 + 769 + pair slack; after the FIR passes the
+                                                            // buffer holds W[290] and, behind it, one half of the window
+                                                            // pair's tensor-core search structures (sc_search_mma.cuh)
+static_assert((FE_BUF - WIN) * sizeof(float2) >= sizeof(SearchMmaB) && (FE_BUF - WIN) * sizeof(float2) >= sizeof(SearchMmaDE),
+              "search structures fit behind W");
+static_assert((FE_BUF * sizeof(float2)) % 16 == 0 && (WIN * sizeof(float2)) % 16 == 0, "16-byte aligned regions");
 constexpr int FE_NPAIR = (FE_NSAMP + 2 + 1) / 2;            // 748 int16 pairs cover any alignment
 constexpr int FE_PAIRS_PER_LANE = (FE_NPAIR + 31) / 32;     // 24
 constexpr int FE_DE_SLOTS = (SEARCH_WORDS + 1) / 2;           // the search operands (floats) in float2 slots
@@ -147,12 +153,14 @@ __device__ __forceinline__ void fe_fir(const float2 *__restrict__ buf, int front
 // coalesced 32-bit pairs.  GENERIC = true: any alignment, scalar 16-bit loads, same arithmetic.
 // rx_timing is 128..255 whenever the front-end runs, so the first sample
 // needed (rx_timing - 48) is never before the frame; it is clamped to keep a corrupt state in bounds.
-template <bool WIDE, bool GENERIC>
+// MMA = true: the search is proposed on the tensor cores and verified exactly (sc_search_mma.cuh), one warp of
+// every warp PAIR doing it for both windows while the other goes on to the barrier; false: all 128 lags exact.
+template <bool WIDE, bool GENERIC, bool MMA>
 __global__ void __launch_bounds__(FE_WARPS * 32, 6)
 frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2 *__restrict__ mix_table,
                 const int *__restrict__ timing_cur, const int *__restrict__ timing_next,
                 float2 *__restrict__ win, int *__restrict__ max_index_out, float *__restrict__ max_value_out,
-                int n_streams) {
+                int n_streams, const uint4 *__restrict__ a_table) {
     __shared__ __align__(16) float2 smem[FE_WARPS][FE_BUF];
     __shared__ int s_maxidx[FE_WARPS];
     __shared__ int s_t2[FE_WARPS];
@@ -224,34 +232,103 @@ frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2
     }
 
     float2 *W = mix;                                        // [290]
-    float *DE = reinterpret_cast<float *>(mix + WIN);       // search operands, sc_search.cuh
-    if (active && lane < FE_FIR_LANES) {
+    if (!MMA) {
+        float *DE = reinterpret_cast<float *>(mix + WIN);   // search operands, sc_search.cuh
+        if (active && lane < FE_FIR_LANES) {
 #pragma unroll
-        for (int r = 0; r < FE_R; r++) {
-            float yr, yi;
-            unpk(accA[r], yr, yi);
-            const float2 wa = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));       // src/fir.c:42
-            unpk(accB[r], yr, yi);
-            const float2 wb = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));
-            const int xa = FE_R * lane + r, xb = FE_PASS_OUT + xa;
-            W[xa] = wa;
-            W[xb] = wb;
-            // ---- stage 3 operands straight from the registers (qpsk.c:88-96, see sc_search.cuh)
-            de_store(DE, xa, wa);
-            if (xb < SEARCH_SYMS) de_store(DE, xb, wb);
+            for (int r = 0; r < FE_R; r++) {
+                float yr, yi;
+                unpk(accA[r], yr, yi);
+                const float2 wa = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));       // src/fir.c:42
+                unpk(accB[r], yr, yi);
+                const float2 wb = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));
+                const int xa = FE_R * lane + r, xb = FE_PASS_OUT + xa;
+                W[xa] = wa;
+                W[xb] = wb;
+                // ---- stage 3 operands straight from the registers (qpsk.c:88-96, see sc_search.cuh)
+                de_store(DE, xa, wa);
+                if (xb < SEARCH_SYMS) de_store(DE, xb, wb);
+            }
         }
-    }
-    __syncwarp();
+        __syncwarp();
 
-    if (active) {
-        int best_idx;
-        float best_val;
-        search_warp(DE, lane, best_idx, best_val);
-        if (lane == 0) {
-            max_index_out[s] = best_idx;
-            max_value_out[s] = best_val;
-            s_maxidx[warp] = best_idx;
-            s_t2[warp] = timing_next[s];
+        if (active) {
+            int best_idx;
+            float best_val;
+            search_warp(DE, lane, best_idx, best_val);
+            if (lane == 0) {
+                max_index_out[s] = best_idx;
+                max_value_out[s] = best_val;
+                s_maxidx[warp] = best_idx;
+                s_t2[warp] = timing_next[s];
+            }
+        }
+    } else {
+        // the pair's structures live behind W in the two warps' buffers: B operand in the even warp's, d/e + lists
+        // in the odd warp's
+        const int pw = warp & 1;
+        SearchMmaB &sb = *reinterpret_cast<SearchMmaB *>(smem[warp & ~1] + WIN);
+        SearchMmaDE &sd = *reinterpret_cast<SearchMmaDE *>(smem[warp | 1] + WIN);
+        // each warp is about to write into its partner's buffer: both must be done with their FIR passes first
+        static_assert(FE_WARPS == 4, "two warp pairs per CTA");
+        if (warp >> 1) asm volatile("bar.sync 2, 64;" ::: "memory");
+        else asm volatile("bar.sync 1, 64;" ::: "memory");
+        float part = 0.0f;
+        if (lane < FE_FIR_LANES) {
+#pragma unroll
+            for (int r = 0; r < FE_R; r++) {
+                float yr, yi;
+                unpk(accA[r], yr, yi);
+                const float2 wa = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));       // src/fir.c:42
+                unpk(accB[r], yr, yi);
+                const float2 wb = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));
+                const int xa = FE_R * lane + r, xb = FE_PASS_OUT + xa;
+                W[xa] = wa;
+                W[xb] = wb;
+                // d = s.r - s.i, e = s.i + s.r: the exact operands of correlate(), qpsk.c:88-96
+                const float da = __fsub_rn(wa.x, wa.y), ea = __fadd_rn(wa.y, wa.x);
+                sd.de[pw][0][xa] = da;
+                sd.de[pw][1][xa] = ea;
+                part = __fadd_rn(part, __fadd_rn(fabsf(da), fabsf(ea)));
+                if (xb < SEARCH_SYMS) {
+                    const float db = __fsub_rn(wb.x, wb.y), eb = __fadd_rn(wb.y, wb.x);
+                    sd.de[pw][0][xb] = db;
+                    sd.de[pw][1][xb] = eb;
+                    part = __fadd_rn(part, __fadd_rn(fabsf(db), fabsf(eb)));
+                }
+            }
+        } else if (lane == FE_FIR_LANES) {
+            sd.de[pw][0][SEARCH_SYMS] = 0.0f;               // x = 255 pads the last bf16 pair
+            sd.de[pw][1][SEARCH_SYMS] = 0.0f;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, off));
+        if (lane == 0) sd.s_abs[pw] = part;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; k++) {                       // bf16 pieces, symbol pairs (x, x + 1)
+            const int x = 2 * lane + 64 * k;
+            const float2 dd = *reinterpret_cast<const float2 *>(&sd.de[pw][0][x]);
+            const float2 ee = *reinterpret_cast<const float2 *>(&sd.de[pw][1][x]);
+            search_mma_stage_pieces(sb, pw, x, dd.x, dd.y, ee.x, ee.y);
+        }
+        // second named barrier of the pair (0 is __syncthreads): the odd warp only signals, the even one waits
+        if (pw == 1) {
+            if (warp >> 1) asm volatile("bar.arrive 4, 64;" ::: "memory");
+            else asm volatile("bar.arrive 3, 64;" ::: "memory");
+        } else {
+            if (warp >> 1) asm volatile("bar.sync 4, 64;" ::: "memory");
+            else asm volatile("bar.sync 3, 64;" ::: "memory");
+            int bi[2];
+            float bv[2];
+            search_mma_pair<true>(sb, sd, a_table, lane, bi, bv);
+            if (lane < 2 && s + lane < n_streams) {
+                const int idx = lane ? bi[1] : bi[0];
+                max_index_out[s + lane] = idx;
+                max_value_out[s + lane] = lane ? bv[1] : bv[0];
+                s_maxidx[warp + lane] = idx;
+                s_t2[warp + lane] = timing_next[s + lane];
+            }
         }
     }
     __syncthreads();
@@ -348,20 +425,23 @@ cudaError_t launch_nco_table(float2 *phase_state, float2 rect, int pattern, int 
 
 cudaError_t launch_frontend(bool wide, const int16_t *in, long stream_stride, const float2 *mix_table,
                             const int *timing_cur, const int *timing_next, float2 *win, int *max_index,
-                            float *max_value, int n_streams, cudaStream_t st) {
+                            float *max_value, int n_streams, cudaStream_t st, const void *search_a_table) {
     const int grid = (n_streams + FE_WARPS - 1) / FE_WARPS;
     const int thr = FE_WARPS * 32;
     // the fast kernel reads the samples as aligned 32-bit pairs: every frame must start on a 4-byte boundary
     const bool generic = ((((uintptr_t) in) & 3) != 0) || ((stream_stride & 1) != 0);
-#define SC_FE_LAUNCH(W, G)                                                                                      \
-    frontend_kernel<W, G><<<grid, thr, 0, st>>>(in, stream_stride, mix_table, timing_cur, timing_next, win, max_index, \
-                                                max_value, n_streams)
+    const uint4 *at = (const uint4 *) search_a_table;
+#define SC_FE_LAUNCH(W, G, M)                                                                                      \
+    frontend_kernel<W, G, M><<<grid, thr, 0, st>>>(in, stream_stride, mix_table, timing_cur, timing_next, win, max_index, \
+                                                   max_value, n_streams, at)
     if (wide) {
-        if (generic) SC_FE_LAUNCH(true, true);
-        else SC_FE_LAUNCH(true, false);
+        if (generic) SC_FE_LAUNCH(true, true, false);
+        else if (at) SC_FE_LAUNCH(true, false, true);
+        else SC_FE_LAUNCH(true, false, false);
     } else {
-        if (generic) SC_FE_LAUNCH(false, true);
-        else SC_FE_LAUNCH(false, false);
+        if (generic) SC_FE_LAUNCH(false, true, false);
+        else if (at) SC_FE_LAUNCH(false, false, true);
+        else SC_FE_LAUNCH(false, false, false);
     }
 #undef SC_FE_LAUNCH
     g_launch_count++;

@@ -42,11 +42,20 @@ constexpr int SM_DE_FLOATS = 2 * PRE + 8;            // d[256] / e[256] (index 2
 // four .b32 registers of lane for Toeplitz tile t, value(r, c) = pre[16 t + c - r] as bf16, 0 outside 0..127.
 static __constant__ uint32_t c_search_pre_neg[4] = {pre_neg_word(0), pre_neg_word(1), pre_neg_word(2), pre_neg_word(3)};
 
-struct SearchMmaSmem {
-    uint32_t bp[8][SM_COL_WORDS];                    // B operand: column n, bf16 pairs in fragment order
+// Shared memory of one window PAIR, in two parts so that the fused front-end can place them in the (dead) sample
+// buffers of the two warps that own the windows.
+struct SearchMmaB {
+    uint32_t bp[8][SM_COL_WORDS];                    // B operand: column n, bf16 pairs in fragment order (4,352 bytes)
+};
+struct SearchMmaDE {
     float de[2][2][SM_DE_FLOATS];                    // [window][d/e][x]
     int cand[2][SM_MAX_CAND];
     int n_cand[2];
+    float s_abs[2];                                  // sum(|d| + |e|) of each window (the fused front-end passes it here)
+};                                                   // 4,312 bytes
+struct SearchMmaSmem {
+    SearchMmaB b;
+    SearchMmaDE d;
 };
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint4 &a, uint32_t b0, uint32_t b1) {
@@ -70,11 +79,8 @@ __device__ __forceinline__ int bp_word(int x) {
 
 // Stage one symbol pair (x, x+1) of window w (0/1): d/e floats for the verifier, bf16 pieces for the proposer.
 // Returns |d|+|e| of both symbols (for the error bound).
-__device__ __forceinline__ float search_mma_stage_pair(SearchMmaSmem &sm, int w, int x, float2 s0, float2 s1) {
-    const float d0 = __fsub_rn(s0.x, s0.y), e0 = __fadd_rn(s0.y, s0.x);       // qpsk.c:88-96 with pre = v(1+i)
-    const float d1 = __fsub_rn(s1.x, s1.y), e1 = __fadd_rn(s1.y, s1.x);
-    *reinterpret_cast<float2 *>(&sm.de[w][0][x]) = make_float2(d0, d1);
-    *reinterpret_cast<float2 *>(&sm.de[w][1][x]) = make_float2(e0, e1);
+// The bf16 pieces of one (d, e) pair of symbols (x, x+1) -> B operand columns of window w.
+__device__ __forceinline__ void search_mma_stage_pieces(SearchMmaB &sb, int w, int x, float d0, float d1, float e0, float e1) {
     uint32_t dh0, dm0, dh1, dm1, eh0, em0, eh1, em1;
     split2(d0, dh0, dm0);
     split2(d1, dh1, dm1);
@@ -82,10 +88,19 @@ __device__ __forceinline__ float search_mma_stage_pair(SearchMmaSmem &sm, int w,
     split2(e1, eh1, em1);
     const int word = bp_word(x);
     // columns: 4w + {0: d_hi, 1: d_mid, 2: e_hi, 3: e_mid}; low half = the lower k (x), high half = x + 1
-    sm.bp[4 * w + 0][word] = __byte_perm(dh0, dh1, 0x7632);
-    sm.bp[4 * w + 1][word] = __byte_perm(dm0, dm1, 0x7632);
-    sm.bp[4 * w + 2][word] = __byte_perm(eh0, eh1, 0x7632);
-    sm.bp[4 * w + 3][word] = __byte_perm(em0, em1, 0x7632);
+    sb.bp[4 * w + 0][word] = __byte_perm(dh0, dh1, 0x7632);
+    sb.bp[4 * w + 1][word] = __byte_perm(dm0, dm1, 0x7632);
+    sb.bp[4 * w + 2][word] = __byte_perm(eh0, eh1, 0x7632);
+    sb.bp[4 * w + 3][word] = __byte_perm(em0, em1, 0x7632);
+}
+
+__device__ __forceinline__ float search_mma_stage_pair(SearchMmaSmem &smem, int w, int x, float2 s0, float2 s1) {
+    SearchMmaDE &sm = smem.d;
+    const float d0 = __fsub_rn(s0.x, s0.y), e0 = __fadd_rn(s0.y, s0.x);       // qpsk.c:88-96 with pre = v(1+i)
+    const float d1 = __fsub_rn(s1.x, s1.y), e1 = __fadd_rn(s1.y, s1.x);
+    *reinterpret_cast<float2 *>(&sm.de[w][0][x]) = make_float2(d0, d1);
+    *reinterpret_cast<float2 *>(&sm.de[w][1][x]) = make_float2(e0, e1);
+    search_mma_stage_pieces(smem.b, w, x, d0, d1, e0, e1);
     return __fadd_rn(__fadd_rn(fabsf(d0), fabsf(e0)), __fadd_rn(fabsf(d1), fabsf(e1)));
 }
 
@@ -187,47 +202,57 @@ __device__ __forceinline__ float search_candidate_threshold(float vmax, float de
     return __fsub_rn(vmax, __fmul_rn(mu, 2.002f));
 }
 
-// Proposer + verifier for the TWO windows staged in sm (window 1 may be all zeros).  All 32 lanes call.
-// s_abs[w] = sum(|d|+|e|) of window w (any lane's copy after a warp reduction).  Results in every lane.
-__device__ __forceinline__ void search_mma_pair(SearchMmaSmem &sm, const uint4 *__restrict__ a_table, int lane,
-                                                const float (&s_abs)[2], int (&best_idx)[2], float (&best_val)[2]) {
+// Proposer + verifier for the TWO windows staged in (sb, sd) (window 1 may be all zeros).  All 32 lanes call;
+// sd.s_abs[w] = sum(|d|+|e|) of window w.  Results in every lane.
+// B_IN_REGS: the 128 lags are done in two halves of 64 with the 12 B fragments of a half held in registers
+// (24 fragment loads instead of 72: for callers that are short of shared-memory bandwidth, i.e. the front-end).
+template <bool B_IN_REGS>
+__device__ __forceinline__ void search_mma_pair(const SearchMmaB &sb, SearchMmaDE &sd, const uint4 *__restrict__ a_table,
+                                                int lane, int (&best_idx)[2], float (&best_val)[2]) {
     const int g = lane >> 2, tid = lane & 3;
-    // ---- propose: OUT[lag][col] = P * X, 72 HMMA
-    // B fragments are re-read from shared memory for every tile (72 conflict-free 64-bit loads): holding all 16
-    // in registers would cost 32 registers and an occupancy step
-    const uint2 *bfrag = reinterpret_cast<const uint2 *>(&sm.bp[g][2 * tid]);
-    float acc[SM_ROWBLOCKS][4];
-#pragma unroll
-    for (int a = 0; a < SM_ROWBLOCKS; a++) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.0f;
-#pragma unroll
-    for (int t = 0; t < SM_TILES; t++) {
-        const uint4 af = __ldg(a_table + t * 32 + lane);
-#pragma unroll
-        for (int a = 0; a < SM_ROWBLOCKS; a++) {
-            const uint2 bf = bfrag[4 * (a + t)];
-            mma_bf16_16816(acc[a], af, bf.x, bf.y);
-        }
-    }
+    const uint2 *bfrag = reinterpret_cast<const uint2 *>(&sb.bp[g][2 * tid]);
     // lane (g, tid): tid 0/1 = re/im of window 0, tid 2/3 = re/im of window 1; rows g and g + 8 of every row block
     const int w = tid >> 1;
     float v[2 * SM_ROWBLOCKS];
     float vmax = 0.0f;
     int imax = 0;
+    // ---- propose: OUT[lag][col] = P * X, 72 HMMA in two halves of 4 row blocks
 #pragma unroll
-    for (int a = 0; a < SM_ROWBLOCKS; a++) {
+    for (int half = 0; half < 2; half++) {
+        constexpr int RB = SM_ROWBLOCKS / 2;
+        float acc[RB][4];
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const float part = __fadd_rn(acc[a][2 * h], acc[a][2 * h + 1]);            // hi + mid piece
-            const float sq = __fmul_rn(part, part);
-            const float val = __fadd_rn(sq, __shfl_xor_sync(0xffffffffu, sq, 1));       // re^2 + im^2
-            v[2 * a + h] = val;
-            if (val > vmax) {
-                vmax = val;
-                imax = 16 * a + 8 * h + g;
+        for (int a = 0; a < RB; a++) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.0f;
+        uint2 bf[RB + SM_TILES - 1];
+        if (B_IN_REGS) {
+#pragma unroll
+            for (int b = 0; b < RB + SM_TILES - 1; b++) bf[b] = bfrag[4 * (RB * half + b)];
+        }
+#pragma unroll
+        for (int t = 0; t < SM_TILES; t++) {
+            const uint4 af = __ldg(a_table + t * 32 + lane);
+#pragma unroll
+            for (int a = 0; a < RB; a++) {
+                const uint2 b2 = B_IN_REGS ? bf[a + t] : bfrag[4 * (RB * half + a + t)];
+                mma_bf16_16816(acc[a], af, b2.x, b2.y);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < RB; a++) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const float part = __fadd_rn(acc[a][2 * h], acc[a][2 * h + 1]);        // hi + mid piece
+                const float sq = __fmul_rn(part, part);
+                const float val = __fadd_rn(sq, __shfl_xor_sync(0xffffffffu, sq, 1));   // re^2 + im^2
+                v[2 * (RB * half + a) + h] = val;
+                if (val > vmax) {
+                    vmax = val;
+                    imax = 16 * (RB * half + a) + 8 * h + g;
+                }
             }
         }
     }
-    // maximum over the 8 row groups (lanes with the same tid)
+    // maximum over the 8 row groups (lanes with the same tid): the warp-reduced argmax of the proposal
 #pragma unroll
     for (int off = 4; off < 32; off <<= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, vmax, off);
@@ -238,15 +263,15 @@ __device__ __forceinline__ void search_mma_pair(SearchMmaSmem &sm, const uint4 *
         }
     }
     // ---- bound and candidates
-    const float thr = search_candidate_threshold(vmax, __fmul_rn(s_abs[w], 0x1.004p-13f));
-    if (lane < 2) sm.n_cand[lane] = 0;
+    const float thr = search_candidate_threshold(vmax, __fmul_rn(sd.s_abs[w], 0x1.004p-13f));
+    if (lane < 2) sd.n_cand[lane] = 0;
     __syncwarp();
     if ((tid & 1) == 0) {
 #pragma unroll
         for (int k = 0; k < 2 * SM_ROWBLOCKS; k++) {
             if (v[k] >= thr) {
-                const int pos = atomicAdd(&sm.n_cand[w], 1);
-                if (pos < SM_MAX_CAND) sm.cand[w][pos] = 16 * (k >> 1) + 8 * (k & 1) + g;
+                const int pos = atomicAdd(&sd.n_cand[w], 1);
+                if (pos < SM_MAX_CAND) sd.cand[w][pos] = 16 * (k >> 1) + 8 * (k & 1) + g;
             }
         }
     }
@@ -255,7 +280,7 @@ __device__ __forceinline__ void search_mma_pair(SearchMmaSmem &sm, const uint4 *
     const int vw = lane >> 4;
     float ev;
     int ei;
-    search_verify16(sm.de[vw][0], sm.de[vw][1], sm.cand[vw], sm.n_cand[vw], lane, ei, ev);
+    search_verify16(sd.de[vw][0], sd.de[vw][1], sd.cand[vw], sd.n_cand[vw], lane, ei, ev);
     // publish window results to every lane
 #pragma unroll
     for (int ww = 0; ww < 2; ww++) {
@@ -265,7 +290,7 @@ __device__ __forceinline__ void search_mma_pair(SearchMmaSmem &sm, const uint4 *
     // ---- fallback: too many candidates (silence, ties over many lags): the full exact search
 #pragma unroll 1
     for (int ww = 0; ww < 2; ww++) {
-        if (sm.n_cand[ww] > SM_MAX_CAND) search_warp_unpadded(sm.de[ww][0], sm.de[ww][1], lane, best_idx[ww], best_val[ww]);
+        if (sd.n_cand[ww] > SM_MAX_CAND) search_warp_unpadded(sd.de[ww][0], sd.de[ww][1], lane, best_idx[ww], best_val[ww]);
     }
 }
 

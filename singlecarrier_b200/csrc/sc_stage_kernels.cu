@@ -299,7 +299,6 @@ search_mma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride, 
     SearchMmaSmem &sm = sm_all[warp];
     const long n_pairs = (n_streams + 1) / 2;
     for (long pr = (long) blockIdx.x * SMM_WARPS + warp; pr < n_pairs; pr += (long) gridDim.x * SMM_WARPS) {
-        float s_abs[2];
         __syncwarp();
         // all 16 loads of the pair are in flight before anything is staged
         float2 v0[2][4], v1[2][4];
@@ -328,12 +327,14 @@ search_mma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride, 
             part[0] = __fadd_rn(part[0], __shfl_xor_sync(0xffffffffu, part[0], off));
             part[1] = __fadd_rn(part[1], __shfl_xor_sync(0xffffffffu, part[1], off));
         }
-        s_abs[0] = part[0];
-        s_abs[1] = part[1];
+        if (lane == 0) {
+            sm.d.s_abs[0] = part[0];
+            sm.d.s_abs[1] = part[1];
+        }
         __syncwarp();
         int bi[2];
         float bv[2];
-        search_mma_pair(sm, a_table, lane, s_abs, bi, bv);
+        search_mma_pair<false>(sm.b, sm.d, a_table, lane, bi, bv);
         if (lane < 2 && 2 * pr + lane < n_streams) {
             max_index[2 * pr + lane] = lane ? bi[1] : bi[0];
             max_value[2 * pr + lane] = lane ? bv[1] : bv[0];

@@ -285,3 +285,27 @@ def test_tensor_core_proposed_search_equals_direct_search(sc, oracle):
         for s in list(range(0, 40)) + list(range(k, k + 150, 7)):                          # and both equal the oracle
             oi, ov = oracle.search(sym[s])
             assert ai[s] == oi and av[s].view(np.uint32) == np.float32(ov).view(np.uint32), s
+
+
+def test_frontend_tensor_core_search_mode_is_bit_identical(sc, oracle):
+    """SC_OPT_FE_SEARCH = SC_FE_SEARCH_MMA: the fused front-end proposes the preamble search on the tensor cores and
+    verifies the candidates exactly; every field of every call equals the default (all-exact) mode and the oracle,
+    on noisy loop-back streams, silence, dead air with exact zeros (many equal correlations) and an odd bank size."""
+    from helpers import compare_results, oracle_results
+    from singlecarrier_b200.modem import FE_SEARCH_MMA, OPT_FE_SEARCH
+    rng = np.random.default_rng(1234)
+    ns, nf = 301, 12
+    samples = synth_streams(oracle, rng, ns, nf)
+    samples[7] = 0                                               # silence: every lag ties at zero
+    samples[8, 5000:] = 0
+    samples[9] = (rng.integers(-3, 4, samples.shape[1])).astype(np.int16)       # near silence (SURVEY pin 7)
+    out = {}
+    for mode in (0, FE_SEARCH_MMA):
+        bank = sc.ModemBank(ns, debug_eq=True)
+        bank.set_option(OPT_FE_SEARCH, mode)
+        out[mode] = bank.rx_frames_host(samples, nf)
+        bank.close()
+    assert out[0][0].tobytes() == out[FE_SEARCH_MMA][0].tobytes()
+    assert out[0][1].tobytes() == out[FE_SEARCH_MMA][1].tobytes()
+    obits, ostats = oracle_results(oracle, samples, nf)
+    assert compare_results(out[FE_SEARCH_MMA][0], out[FE_SEARCH_MMA][1], obits, ostats) == []
