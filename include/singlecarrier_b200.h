@@ -312,6 +312,17 @@ int sc_comm_unique_id(void *id128);                                 /* ncclGetUn
 int sc_comm_init_rank(void **comm, int n_ranks, int rank, const void *id128, int device);
 int sc_comm_init_all(void **comms, int n_devices, const int *devices);  /* one process, n GPUs */
 int sc_comm_destroy(void *comm);
+int sc_comm_group_start(void);          /* ncclGroupStart/End: one process issuing the reduce of several ranks */
+int sc_comm_group_end(void);
+
+/* ---- device memory for callers without a CUDA binding (plain C, cgo, Rust FFI) ------------------------------ */
+int sc_device_malloc(int device, size_t bytes, void **ptr);        /* zero-filled */
+int sc_device_free(int device, void *ptr);
+#define SC_COPY_H2D 0
+#define SC_COPY_D2H 1
+#define SC_COPY_D2D 2
+int sc_device_copy(int device, void *dst, const void *src, size_t bytes, int kind);   /* synchronous */
+int sc_device_synchronize(int device);
 
 /* ---- host memory and the PCIe ceiling -------------------------------------------------------------------- */
 

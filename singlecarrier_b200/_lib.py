@@ -81,6 +81,12 @@ def _load() -> C.CDLL:
     sig("sc_comm_init_rank", i32, C.POINTER(vp), i32, i32, vp, i32)
     sig("sc_comm_init_all", i32, C.POINTER(vp), i32, C.POINTER(i32))
     sig("sc_comm_destroy", i32, vp)
+    sig("sc_comm_group_start", i32)
+    sig("sc_comm_group_end", i32)
+    sig("sc_device_malloc", i32, i32, C.c_size_t, C.POINTER(vp))
+    sig("sc_device_free", i32, i32, vp)
+    sig("sc_device_copy", i32, i32, vp, vp, C.c_size_t, i32)
+    sig("sc_device_synchronize", i32, i32)
     sig("sc_host_alloc", i32, C.POINTER(vp), C.c_size_t, i32, C.POINTER(i32))
     sig("sc_host_free", i32, vp)
     sig("sc_host_register", i32, vp, C.c_size_t)

@@ -202,6 +202,7 @@ typedef int (*fn_comm_init_all)(void **, int, const int *);
 typedef int (*fn_comm_destroy)(void *);
 typedef int (*fn_all_reduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
 typedef const char *(*fn_get_error_string)(int);
+typedef int (*fn_group)(void);
 const int NCCL_UINT64 = 5, NCCL_SUM = 0;               // ncclDataType_t / ncclRedOp_t values, nccl.h
 
 struct Nccl {
@@ -212,6 +213,7 @@ struct Nccl {
     fn_comm_destroy comm_destroy = nullptr;
     fn_all_reduce all_reduce = nullptr;
     fn_get_error_string error_string = nullptr;
+    fn_group group_start = nullptr, group_end = nullptr;
     std::once_flag once;
     std::string why;
 } g_nccl;
@@ -233,8 +235,10 @@ void nccl_bind() {
     g_nccl.comm_destroy = (fn_comm_destroy) dlsym(h, "ncclCommDestroy");
     g_nccl.all_reduce = (fn_all_reduce) dlsym(h, "ncclAllReduce");
     g_nccl.error_string = (fn_get_error_string) dlsym(h, "ncclGetErrorString");
+    g_nccl.group_start = (fn_group) dlsym(h, "ncclGroupStart");
+    g_nccl.group_end = (fn_group) dlsym(h, "ncclGroupEnd");
     if (!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.comm_init_all || !g_nccl.comm_destroy ||
-        !g_nccl.all_reduce) {
+        !g_nccl.all_reduce || !g_nccl.group_start || !g_nccl.group_end) {
         g_nccl.why = "libnccl.so.2 lacks an expected symbol";
         g_nccl.lib = nullptr;
     }
@@ -294,4 +298,50 @@ extern "C" int sc_reduce_stats(uint64_t *counters, int n_counters, void *nccl_co
     if (rc != SC_OK) return rc;
     return nccl_check(g_nccl.all_reduce(counters, counters, (size_t) n_counters, NCCL_UINT64, NCCL_SUM, nccl_comm,
                                         (cudaStream_t) stream), "ncclAllReduce");
+}
+
+// one process driving several ranks brackets their sc_reduce_stats calls with these (ncclGroupStart/End)
+extern "C" int sc_comm_group_start(void) {
+    int rc = nccl_ready();
+    if (rc != SC_OK) return rc;
+    return nccl_check(g_nccl.group_start(), "ncclGroupStart");
+}
+extern "C" int sc_comm_group_end(void) {
+    int rc = nccl_ready();
+    if (rc != SC_OK) return rc;
+    return nccl_check(g_nccl.group_end(), "ncclGroupEnd");
+}
+
+// ---- device memory for callers without a CUDA binding (plain C, Go, Rust ...) -------------------------
+extern "C" int sc_device_malloc(int device, size_t bytes, void **ptr) {
+    if (!ptr || bytes == 0) return api_fail(SC_EINVAL, "sc_device_malloc: bad arguments");
+    *ptr = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return api_fail(SC_ECUDA, "sc_device_malloc: no CUDA device");
+    }
+    if (device < 0 || device >= ndev) return api_fail(SC_EINVAL, "sc_device_malloc: bad device");
+    HCU(cudaSetDevice(device));
+    HCU(cudaMalloc(ptr, bytes));
+    HCU(cudaMemset(*ptr, 0, bytes));
+    return SC_OK;
+}
+extern "C" int sc_device_free(int device, void *ptr) {
+    if (!ptr) return SC_OK;
+    HCU(cudaSetDevice(device));
+    HCU(cudaFree(ptr));
+    return SC_OK;
+}
+extern "C" int sc_device_copy(int device, void *dst, const void *src, size_t bytes, int kind) {
+    if (!dst || !src || kind < 0 || kind > 2) return api_fail(SC_EINVAL, "sc_device_copy: bad arguments");
+    HCU(cudaSetDevice(device));
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    HCU(cudaMemcpy(dst, src, bytes, k));
+    return SC_OK;
+}
+extern "C" int sc_device_synchronize(int device) {
+    HCU(cudaSetDevice(device));
+    HCU(cudaDeviceSynchronize());
+    return SC_OK;
 }

@@ -183,3 +183,29 @@ def test_batched_c_example(tmp_path, oracle, gold):
                 want.append(f"stream {k} call {n} matches {st['matches'][n]} max_index {st['max_index'][n]} "
                             f"max_value {st['max_value'][n]:.2f} bits " + "".join(map(str, bits[n])))
     assert out[:-1] == want and out[-1].startswith(f"3 streams x {nf} calls")
+
+
+def test_reduce_c_example(tmp_path, oracle, gold):
+    """examples/reduce_2gpu.c: shard -> demodulate -> count on the device -> ONE NCCL all-reduce, all through the C ABI
+    from plain C (no CUDA headers).  Uses min(2, visible GPUs) ranks; every rank must print the job's totals."""
+    exe = tmp_path / "reduce_2gpu"
+    libdir = os.path.join(ROOT, "singlecarrier_b200")
+    subprocess.run(["gcc", "-std=gnu11", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "reduce_2gpu.c"), "-o", str(exe), "-L", libdir,
+                    "-lsinglecarrier_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    ns = 6
+    out = subprocess.run([str(exe), os.path.join(ROOT, "tests", "golden", "preamble_qpsk_8k.raw"), str(ns)], check=True,
+                         capture_output=True, text=True, timeout=300).stdout.strip().splitlines()
+    x = gold("preamble_qpsk_8k.raw")
+    nf = (x.size + 3 * ns) // 1880 + 2
+    calls = valid = matches = 0
+    for k in range(ns):
+        s = np.zeros(nf * 1880, np.int16)
+        s[3 * k:3 * k + x.size] = x
+        _, st = oracle.run_stream(s)
+        calls += nf
+        valid += int(st["valid"].sum())
+        matches += int(st["matches"].sum())
+    assert 1 <= len(out) <= 2
+    for ln in out:
+        assert f"calls {calls} valid {valid} sum_matches {matches} " in ln, (ln, calls, valid, matches)
