@@ -105,22 +105,29 @@ int qpsk_tx_frame(int16_t samples[], complex float symbol[], int length, bool pr
 }
 
 /* ---- fft.h: configuration objects keep the reference's public layout ------------------------------ */
-fft_cfg fft_alloc(int nfft, int inverse_fft, void *mem, size_t *lenmem) {
-    fft_cfg st = NULL;
-    size_t memneeded = sizeof (struct fft_state) + sizeof (complex float) * (size_t) (nfft - 1);
 
-    if (lenmem == NULL) {
-        st = (fft_cfg) malloc(memneeded);
-    } else {
-        if (mem != NULL && *lenmem >= memneeded) st = (fft_cfg) mem;
-        *lenmem = memneeded;
-    }
-    if (st != NULL) {
-        st->nfft = nfft;
-        st->inverse = inverse_fft;
-        scl_twiddles(nfft, inverse_fft, (float *) st->twiddles);
-        scl_kf_factor(nfft, st->factors);
-    }
+/* bytes of a struct fft_state for n points: the struct ends in twiddles[1], so n - 1 more follow it */
+static size_t fft_state_bytes(int n) { return sizeof (struct fft_state) + sizeof (complex float) * (size_t) (n - 1); }
+
+/* The reference's placement protocol (src/fft.c:57-64, 98-106): lenmem == NULL -> malloc; otherwise use the
+ * caller's block if it is large enough, and always report the size needed through *lenmem. */
+static void *place(void *mem, size_t *lenmem, size_t need) {
+    if (lenmem == NULL) return malloc(need);
+    void *p = (mem != NULL && *lenmem >= need) ? mem : NULL;
+    *lenmem = need;
+    return p;
+}
+
+static void fft_state_fill(fft_cfg st, int nfft, int inverse_fft) {
+    st->nfft = nfft;
+    st->inverse = inverse_fft;
+    scl_twiddles(nfft, inverse_fft, (float *) st->twiddles);     /* same libm expressions as src/fft.c:70-77 */
+    scl_kf_factor(nfft, st->factors);                            /* kf_factor(), src/fft.c:433-459 */
+}
+
+fft_cfg fft_alloc(int nfft, int inverse_fft, void *mem, size_t *lenmem) {
+    fft_cfg st = (fft_cfg) place(mem, lenmem, fft_state_bytes(nfft));
+    if (st != NULL) fft_state_fill(st, nfft, inverse_fft);
     return st;
 }
 
@@ -129,27 +136,21 @@ void fft(fft_cfg cfg, const complex float *fin, complex float *fout) {
                  (float *) fout), "fft");
 }
 
+/* One block: [struct fftr_state][fft_state for nfft/2 points][tmpbuf: nfft/2][super_twiddles: nfft/4], the layout
+ * callers of the reference may rely on (headers/fft.h:33-41, src/fft.c:85-131). */
 fftr_cfg fftr_alloc(int nfft, int inverse_fft, void *mem, size_t *lenmem) {
-    fftr_cfg st = NULL;
-    size_t subsize = 0;
-
     if (nfft & 1) return NULL;                       /* src/fft.c:89-91 */
-    nfft >>= 1;
-    fft_alloc(nfft, inverse_fft, NULL, &subsize);
-    size_t memneeded = sizeof (struct fftr_state) + subsize + sizeof (complex float) * (size_t) (nfft * 3 / 2);
-
-    if (lenmem == NULL) {
-        st = (fftr_cfg) malloc(memneeded);
-    } else {
-        if (mem != NULL && *lenmem >= memneeded) st = (fftr_cfg) mem;
-        *lenmem = memneeded;
-    }
+    const int half = nfft / 2;
+    const size_t sub = fft_state_bytes(half);
+    const size_t need = sizeof (struct fftr_state) + sub + sizeof (complex float) * (size_t) (half * 3 / 2);
+    fftr_cfg st = (fftr_cfg) place(mem, lenmem, need);
     if (st == NULL) return NULL;
-    st->substate = (fft_cfg) (st + 1);
-    st->tmpbuf = (complex float *) (((char *) st->substate) + subsize);
-    st->super_twiddles = st->tmpbuf + nfft;
-    fft_alloc(nfft, inverse_fft, st->substate, &subsize);
-    scl_super_twiddles(nfft, inverse_fft, (float *) st->super_twiddles);
+    char *base = (char *) (st + 1);
+    st->substate = (fft_cfg) base;
+    st->tmpbuf = (complex float *) (base + sub);
+    st->super_twiddles = st->tmpbuf + half;
+    fft_state_fill(st->substate, half, inverse_fft);
+    scl_super_twiddles(half, inverse_fft, (float *) st->super_twiddles);
     return st;
 }
 

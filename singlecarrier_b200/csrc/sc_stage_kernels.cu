@@ -291,7 +291,7 @@ search_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride, int 
 // ------------------------------------------------------------------------------------------------
 constexpr int SMM_WARPS = 4;
 
-__global__ void __launch_bounds__(SMM_WARPS * 32, 6)
+__global__ void __launch_bounds__(SMM_WARPS * 32, 5)
 search_mma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride, const uint4 *__restrict__ a_table,
                         int *__restrict__ max_index, float *__restrict__ max_value, long n_streams) {
     __shared__ __align__(16) SearchMmaSmem sm_all[SMM_WARPS];
@@ -334,7 +334,7 @@ search_mma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride, 
         __syncwarp();
         int bi[2];
         float bv[2];
-        search_mma_pair<false>(sm.b, sm.d, a_table, lane, bi, bv);
+        search_mma_pair<true>(sm.b, sm.d, a_table, lane, bi, bv);    // B fragments in registers: the kernel is LSU-bound
         if (lane < 2 && 2 * pr + lane < n_streams) {
             max_index[2 * pr + lane] = lane ? bi[1] : bi[0];
             max_value[2 * pr + lane] = lane ? bv[1] : bv[0];
@@ -489,7 +489,7 @@ void search_mma_make_table(uint32_t *table /* [9][32][4] */) {
 cudaError_t launch_search_mma_batch(long n_streams, const float2 *symbols, long symbol_stride, const void *a_table,
                                     int *max_index, float *max_value, cudaStream_t st) {
     const long n_pairs = (n_streams + 1) / 2;
-    const int grid = (int) std::min<long>((n_pairs + SMM_WARPS - 1) / SMM_WARPS, 148L * 6);     // one resident wave
+    const int grid = (int) std::min<long>((n_pairs + SMM_WARPS - 1) / SMM_WARPS, 148L * 5);     // one resident wave
     search_mma_batch_kernel<<<grid, SMM_WARPS * 32, 0, st>>>(symbols, symbol_stride, (const uint4 *) a_table, max_index,
                                                              max_value, n_streams);
     g_launch_count++;
