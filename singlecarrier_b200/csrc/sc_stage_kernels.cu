@@ -19,107 +19,29 @@ namespace sc {
 
 // ------------------------------------------------------------------------------------------------
 // fir(): 49-tap real-coefficient FIR on complex samples, in place, caller-owned delay line holding
-// the RAW past inputs, output scaled by GAIN.  One WARP per stream walks the samples in tiles of
-// 160 (32 lanes x 5 consecutive outputs; lane stride 5 slots => conflict-free LDS.64) with the last
-// 49 raw inputs carried in shared memory between tiles, so each sample is read and written once and
-// only __syncwarp() is needed; 32 warps per SM hide the global-memory latency of each other's tiles.
+// the RAW past inputs, output scaled by GAIN.  One WARP per stream walks the samples in tiles with the
+// last 49 raw inputs carried in shared memory between tiles, so each sample is read and written once
+// and only __syncwarp() is needed.
 // ext[0..48] = memory[0..48] (oldest first), ext[49 + j] = sample[j];
 // out[j] = GAIN * sum_k ext[j + 1 + k] * coeff[k], k ascending (src/fir.c:36-42).
 //
 // FAST = true is the explicitly named tolerance mode (SC_FIR_FAST): the multiply-add is contracted
 // into one FFMA2, which halves the FP32 work, at the price of last-bit differences from the
 // reference (never used on the parity path).
-// ------------------------------------------------------------------------------------------------
-constexpr int FIR_WARPS = 8;
-constexpr int FIR_R = 5;
-constexpr int FIR_TILE = 32 * FIR_R;                   // 160
-
+//
 // Tile pipeline of one warp (both modes):
-//   registers  <- global   the NEXT tile's 160 raw samples (5 coalesced 256-byte loads), issued before this
-//                          tile's arithmetic so the DRAM latency hides behind it (cp.async into rotating buffers
-//                          was measured 8 % slower: 8-byte LDGSTS is the less efficient path);
-//   ext[49..]  <- registers, __syncwarp, 49 + 4 LDS.64 and 245 packed multiply-adds per lane;
+//   registers  <- global   the NEXT tile's raw samples, issued before this tile's arithmetic so the DRAM latency
+//                          hides behind it (cp.async into rotating buffers was measured 8 % slower);
+//   ext[49..]  <- registers, __syncwarp, the window loads and the packed multiply-adds;
 //   obuf       <- results  (obuf is ext + 49: every lane has finished reading by then), carry -> ext[0..48];
-//   global     <- obuf     5 coalesced 256-byte stores per warp (a lane's own 5 outputs are 40 bytes apart,
-//                          which would cost five partial-sector stores per 32-byte sector).
-template <bool WIDE, bool FAST>
-__global__ void __launch_bounds__(FIR_WARPS * 32, 4)
-fir_batch_kernel(float2 *__restrict__ memory, float2 *__restrict__ sample, long sample_stride, int length,
-                 long n_streams) {
-    __shared__ __align__(16) float2 ext_all[FIR_WARPS][NTAPS + FIR_TILE + 7];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float2 *ext = ext_all[warp];
-    float2 *obuf = ext + NTAPS;
-    for (long s = (long) blockIdx.x * FIR_WARPS + warp; s < n_streams; s += (long) gridDim.x * FIR_WARPS) {
-        float2 *mem = memory + s * NTAPS;
-        float2 *x = sample + s * sample_stride;
-        __syncwarp();
-        for (int i = lane; i < NTAPS; i += 32) ext[i] = mem[i];
-        float2 nxt[FIR_R];
-#pragma unroll
-        for (int k = 0; k < FIR_R; k++) {
-            const int j = lane + 32 * k;
-            nxt[k] = j < length ? x[j] : make_float2(0.f, 0.f);
-        }
-        for (int t0 = 0; t0 < length; t0 += FIR_TILE) {
-            const int n = min(FIR_TILE, length - t0);
-#pragma unroll
-            for (int k = 0; k < FIR_R; k++) ext[NTAPS + lane + 32 * k] = nxt[k];
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < FIR_R; k++) {                                    // next tile's loads fly during the math
-                const int j = t0 + FIR_TILE + lane + 32 * k;
-                nxt[k] = j < length ? x[j] : make_float2(0.f, 0.f);
-            }
-            u64 acc[FIR_R];
-#pragma unroll
-            for (int r = 0; r < FIR_R; r++) acc[r] = 0ull;
-            {
-                const u64 *ep = reinterpret_cast<const u64 *>(ext) + FIR_R * lane + 1;
-#pragma unroll
-                for (int j = 0; j < NTAPS + FIR_R - 1; j++) {
-                    const u64 v = ep[j];
-#pragma unroll
-                    for (int r = 0; r < FIR_R; r++) {
-                        const int k = j - r;
-                        if (k >= 0 && k < NTAPS) {
-                            if (FAST) acc[r] = pk_fma_bcast(v, tap<WIDE>(k), acc[r]);
-                            else acc[r] = pk_add(acc[r], pk_mul_bcast_pz(v, tap<WIDE>(k)));
-                        }
-                    }
-                }
-            }
-            // the last 49 raw inputs become the head of the next tile
-            float2 c0 = ext[n + lane], c1 = make_float2(0.f, 0.f);
-            if (lane + 32 < NTAPS) c1 = ext[n + lane + 32];
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < FIR_R; r++) {
-                float yr, yi;
-                unpk(acc[r], yr, yi);
-                obuf[FIR_R * lane + r] = make_float2(__fmul_rn(yr, FIR_GAIN), __fmul_rn(yi, FIR_GAIN));
-            }
-            ext[lane] = c0;
-            if (lane + 32 < NTAPS) ext[lane + 32] = c1;
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < FIR_R; k++) {
-                const int j = lane + 32 * k;
-                if (j < n) x[t0 + j] = obuf[j];
-            }
-        }
-        __syncwarp();
-        for (int i = lane; i < NTAPS; i += 32) mem[i] = ext[i];
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// The same pipeline with 10 outputs per lane (tiles of 320) and 128-bit shared-memory loads: each staged
-// sample is then read by 5.8 lanes instead of 10.6, which is what the contracted (FAST) mode needs -- with
-// half the arithmetic per sample it is bound by the shared-memory data pipe (ncu: 90 % at 5 outputs per
-// lane), not by the FP32 pipe.  buf[1 + i] holds ext[i], so that every lane's window (10 lane + 2) and its
-// 10 outputs (50 + 10 lane) start on a 16-byte boundary; lane stride 80 bytes = 5 x 16 is odd in 16-byte
-// units, hence conflict-free for LDS.128 / STS.128.
+//   global     <- obuf     coalesced stores (a lane's own outputs are 40 / 80 bytes apart: stored directly they
+//                          would cost several partial-sector stores per 32-byte sector).
+//
+// 10 outputs per lane (tiles of 320) and 128-bit shared-memory loads: each staged sample is read by 5.8 lanes
+// (10.6 with 5 outputs per lane, the round-1 form), which is what the contracted mode needs -- with half the
+// arithmetic per sample it was bound by the shared-memory data pipe (ncu: 90 %), not by the FP32 pipe.
+// buf[1 + i] holds ext[i], so that every lane's window (10 lane + 2) and its 10 outputs (50 + 10 lane) start on a
+// 16-byte boundary; lane stride 80 bytes = 5 x 16 is odd in 16-byte units, hence conflict-free for LDS.128 / STS.128.
 // ------------------------------------------------------------------------------------------------
 constexpr int FIR10_WARPS = 4;
 constexpr int FIR10_R = 10;
@@ -234,29 +156,18 @@ fir_batch10_kernel(float2 *__restrict__ memory, float2 *__restrict__ sample, lon
 
 cudaError_t launch_fir_batch(bool wide, long n_streams, float2 *memory, float2 *sample, long sample_stride,
                              int length, cudaStream_t st, bool fast) {
-    static const bool use_r5 = getenv("SC_FIR_R5") != nullptr;        // the 5-outputs-per-lane kernel, for comparison
-    if (use_r5) {
-        const int grid = (int) std::min<long>((n_streams + FIR_WARPS - 1) / FIR_WARPS, 148L * 4);
-        const int thr = FIR_WARPS * 32;
-        if (fast) {
-            if (wide) fir_batch_kernel<true, true><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams);
-            else fir_batch_kernel<false, true><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams);
-        } else if (wide) fir_batch_kernel<true, false><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams);
-        else fir_batch_kernel<false, false><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams);
-    } else {
-        const int grid = (int) std::min<long>((n_streams + FIR10_WARPS - 1) / FIR10_WARPS, 148L * 6);
-        const int thr = FIR10_WARPS * 32;
-        const bool vec = (((uintptr_t) sample) & 15) == 0 && (sample_stride & 1) == 0;
+    const int grid = (int) std::min<long>((n_streams + FIR10_WARPS - 1) / FIR10_WARPS, 148L * 6);
+    const int thr = FIR10_WARPS * 32;
+    const bool vec = (((uintptr_t) sample) & 15) == 0 && (sample_stride & 1) == 0;
 #define SC_FIR_LAUNCH(W, F, V) fir_batch10_kernel<W, F, V><<<grid, thr, 0, st>>>(memory, sample, sample_stride, length, n_streams)
-        if (wide) {
-            if (fast) { if (vec) SC_FIR_LAUNCH(true, true, true); else SC_FIR_LAUNCH(true, true, false); }
-            else { if (vec) SC_FIR_LAUNCH(true, false, true); else SC_FIR_LAUNCH(true, false, false); }
-        } else {
-            if (fast) { if (vec) SC_FIR_LAUNCH(false, true, true); else SC_FIR_LAUNCH(false, true, false); }
-            else { if (vec) SC_FIR_LAUNCH(false, false, true); else SC_FIR_LAUNCH(false, false, false); }
-        }
-#undef SC_FIR_LAUNCH
+    if (wide) {
+        if (fast) { if (vec) SC_FIR_LAUNCH(true, true, true); else SC_FIR_LAUNCH(true, true, false); }
+        else { if (vec) SC_FIR_LAUNCH(true, false, true); else SC_FIR_LAUNCH(true, false, false); }
+    } else {
+        if (fast) { if (vec) SC_FIR_LAUNCH(false, true, true); else SC_FIR_LAUNCH(false, true, false); }
+        else { if (vec) SC_FIR_LAUNCH(false, false, true); else SC_FIR_LAUNCH(false, false, false); }
     }
+#undef SC_FIR_LAUNCH
     g_launch_count++;
     return cudaGetLastError();
 }
