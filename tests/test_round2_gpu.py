@@ -307,5 +307,13 @@ def test_frontend_tensor_core_search_mode_is_bit_identical(sc, oracle):
         bank.close()
     assert out[0][0].tobytes() == out[FE_SEARCH_MMA][0].tobytes()
     assert out[0][1].tobytes() == out[FE_SEARCH_MMA][1].tobytes()
+    # the proposer's table is a process-wide cache: releasing it between two batches of a live handle is harmless
+    bank = sc.ModemBank(ns, debug_eq=True)
+    bank.set_option(OPT_FE_SEARCH, FE_SEARCH_MMA)
+    a = bank.rx_frames_host(np.ascontiguousarray(samples[:, : 6 * 1880]), 6)
+    sc._lib.check(sc.lib.sc_release_caches())
+    b = bank.rx_frames_host(np.ascontiguousarray(samples[:, 6 * 1880:]), nf - 6)
+    bank.close()
+    assert np.concatenate([a[0], b[0]], axis=1).tobytes() == out[0][0].tobytes()
     obits, ostats = oracle_results(oracle, samples, nf)
     assert compare_results(out[FE_SEARCH_MMA][0], out[FE_SEARCH_MMA][1], obits, ostats) == []
