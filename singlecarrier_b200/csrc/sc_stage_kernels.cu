@@ -1,6 +1,6 @@
 // sc_stage_kernels.cu -- batched forms of the reference's L1 primitives as stand-alone kernels
 // (the stage entry points of include/singlecarrier_b200.h and the back end of the drop-in symbols).
-//   fir_batch_kernel     fir()                            src/fir.c:22-44
+//   fir_batch10_kernel   fir()                            src/fir.c:22-44
 //   search_batch_kernel  correlate() + argmax             src/qpsk.c:88-96, 172-183
 //   track_window_kernel  kalman_reset .. data_eq loop     src/qpsk.c:186-238
 #include "sc_common.cuh"

