@@ -102,6 +102,14 @@ uint64_t sc_launch_count(void);
 #define SC_OPT_FE_SEARCH     4
 #define SC_FE_SEARCH_DIRECT  0   /* all 128 lags with the exact sequential sums                                   */
 #define SC_FE_SEARCH_MMA     1   /* proposed on the tensor cores, the candidates verified with the exact sums      */
+/* SC_OPT_TRACKER: which kernel runs the per-stream equalizer loop.  Identical results either way: the lane-
+ * cooperative kernel executes the same operations in the same order, 16 lanes per stream, and is what makes a
+ * bank too small to fill the GPU with one thread per stream 3x faster per call. */
+#define SC_OPT_TRACKER       5
+#define SC_TRACKER_AUTO      0   /* cooperative up to SC_TRACKER_COOP_MAX streams per launch, else one thread each */
+#define SC_TRACKER_THREAD    1
+#define SC_TRACKER_COOP      2
+#define SC_TRACKER_COOP_MAX  8192
 int  sc_set_option(sc_modem *m, int option, int64_t value);
 int  sc_profile_read(sc_modem *m, double out[4]);
 /* bytes queued host->device (out[0]) and device->host (out[1]) by sc_rx_frames_host since sc_create */

@@ -22,7 +22,7 @@ cudaError_t launch_frontend(bool wide, const int16_t *in, long stream_stride, co
 cudaError_t launch_track(bool debug_eq, const float2 *win, const int *max_index, const float *max_value,
                          const int *timing_cur, int *timing_next, sc_frame_result *results, long result_stride,
                          float *eq_dbg, float *state_dbg, uint32_t call_index, unsigned long long keystream,
-                         int n_streams, cudaStream_t st);
+                         int n_streams, cudaStream_t st, bool coop = false);
 constexpr int TRACK_STATE_FLOATS = 48;   // C[5], G[5], U[10] complex, D[5], KY, 2 pad: the drop-in shim's view
 
 // sc_stage_kernels.cu

@@ -14,6 +14,7 @@
 #include "sc_search.cuh"
 #include "sc_search_mma.cuh"
 #include "sc_track_core.cuh"
+#include "sc_tracker_coop.cuh"
 #include "sc_kernels.h"
 
 #include <stdlib.h>
@@ -413,6 +414,90 @@ track_kernel(const float2 *__restrict__ win, const int *__restrict__ max_index, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// track_coop_kernel: the same call, 16 lanes per stream (sc_tracker_coop.cuh) -- for banks too small to fill
+// the GPU with one thread per stream, where the tracker's dependent chain is the whole cost of a call.
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_THREADS = 64;
+
+__global__ void __launch_bounds__(TC_THREADS)
+track_coop_kernel(const float2 *__restrict__ win, const int *__restrict__ max_index, const float *__restrict__ max_value,
+                  const int *__restrict__ timing_cur, int *__restrict__ timing_next,
+                  sc_frame_result *__restrict__ results, long result_stride, uint32_t call_index,
+                  unsigned long long keystream, int n_streams) {
+    const int lane = threadIdx.x & 31;
+    const long s_raw = ((long) blockIdx.x * TC_THREADS + threadIdx.x) / TC_LANES;
+    const bool live = s_raw < n_streams;
+    const long s = live ? s_raw : n_streams - 1;                   // every lane stays in the shuffles
+
+    CoopTracker tk;
+    tk.init(lane);
+    tk.reset();                                                    // qpsk.c:186
+
+    // The window is 198 rows of 8 bytes in L2 (the front-end has just written it), ~700 clocks away; a step is ~200.
+    // All of it is fetched at once into shared memory (13 loads in flight per lane), then read from there.
+    __shared__ float2 s_win[TC_THREADS / TC_LANES][WIN_ROWS + 2];
+    float2 *W = s_win[threadIdx.x / TC_LANES];
+    {
+        const float2 *X = win + ((s >> 5) * WIN_ROWS) * 32 + (s & 31);
+        const int g = lane & (TC_LANES - 1);
+#pragma unroll
+        for (int r = 0; r < (WIN_ROWS + TC_LANES - 1) / TC_LANES; r++) {
+            const int row = g + r * TC_LANES;
+            if (row < WIN_ROWS) W[row] = __ldg(X + row * 32);
+        }
+    }
+    __syncwarp();
+    const float2 *Xi = W + tk.myi, *Xj = W + tk.myj;
+
+    // equalize(), qpsk.c:111-123, and magnitude(), qpsk.c:101-109 (the sum over x[0] is kept by lanes with myi == 0)
+    int matches = 0, bI, bQ;
+    float mag = 0.0f;
+    c32 xi = from2(Xi[0]), xj = from2(Xj[0]);
+#pragma unroll 2
+    for (int k = 0; k < PRE; k++) {
+        const c32 ni = from2(Xi[k + 1]), nj = from2(Xj[k + 1]);
+        const float ref = ((c_pre_neg[k >> 5] >> (k & 31)) & 1u) ? -1.0f : 1.0f;
+        mag = __fadd_rn(mag, __fadd_rn(__fmul_rn(xi.r, xi.r), __fmul_rn(xi.i, xi.i)));
+        const float er = tk.step<false>(xi, xj, ref, bI, bQ);
+        if (__fmul_rn(er, ref) > 0.0f) matches++;
+        xi = ni;
+        xj = nj;
+    }
+    const bool valid = matches > MATCH_THRESHOLD;                  // qpsk.c:196
+
+    // valid: data symbols follow the preamble; invalid: they start at rx_timing
+    const int row0 = valid ? PRE : X_ROWS;
+    Xi += row0;
+    Xj += row0;
+    xi = from2(Xi[0]);
+    xj = from2(Xj[0]);
+    unsigned long long word = 0ull;
+    float cost = 0.0f;
+#pragma unroll 1
+    for (int k = 0; k < NDATA; k++) {
+        const c32 ni = from2(Xi[k + 1]), nj = from2(Xj[k + 1]);    // at most row 197 + 1: inside the padded array
+        const float er = tk.step<true>(xi, xj, 0.0f, bI, bQ);
+        cost = __fadd_rn(cost, er);                                // qpsk.c:228
+        word |= ((unsigned long long) (unsigned) (bQ | (bI << 1))) << (2 * k);
+        xi = ni;
+        xj = nj;
+    }
+
+    if (live && (lane & (TC_LANES - 1)) == 10) {                   // column lane 0: myi == 0, so mag is the real sum
+        TrackOut o;
+        o.word = word;
+        o.cost = valid ? mag : cost;
+        o.matches = matches;
+        o.valid = valid;
+        const int t_in = timing_cur[s];
+        const int mi = max_index[s];
+        const int t_out = valid ? mi + PRE : t_in;                 // qpsk.c:219
+        timing_next[s] = t_out;
+        store_result(results + s * result_stride, o, keystream, max_value[s], mi, t_out, call_index);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-side launchers (called from sc_api.cu)
 // ------------------------------------------------------------------------------------------------
 
@@ -451,7 +536,14 @@ cudaError_t launch_frontend(bool wide, const int16_t *in, long stream_stride, co
 cudaError_t launch_track(bool debug_eq, const float2 *win, const int *max_index, const float *max_value,
                          const int *timing_cur, int *timing_next, sc_frame_result *results, long result_stride,
                          float *eq_dbg, float *state_dbg, uint32_t call_index, unsigned long long keystream,
-                         int n_streams, cudaStream_t st) {
+                         int n_streams, cudaStream_t st, bool coop) {
+    if (coop && !debug_eq) {
+        const long threads = (long) n_streams * TC_LANES;
+        track_coop_kernel<<<(int) ((threads + TC_THREADS - 1) / TC_THREADS), TC_THREADS, 0, st>>>(
+            win, max_index, max_value, timing_cur, timing_next, results, result_stride, call_index, keystream, n_streams);
+        g_launch_count++;
+        return cudaGetLastError();
+    }
     const int thr = TK_THREADS;                 // 32 / 64 / 128 measured equal within 0.3 %
     const int grid = (n_streams + thr - 1) / thr;
     if (debug_eq)

@@ -317,3 +317,29 @@ def test_frontend_tensor_core_search_mode_is_bit_identical(sc, oracle):
     assert np.concatenate([a[0], b[0]], axis=1).tobytes() == out[0][0].tobytes()
     obits, ostats = oracle_results(oracle, samples, nf)
     assert compare_results(out[FE_SEARCH_MMA][0], out[FE_SEARCH_MMA][1], obits, ostats) == []
+
+
+def test_lane_cooperative_tracker_is_bit_identical(sc, oracle):
+    """SC_OPT_TRACKER: the 16-lanes-per-stream tracker (the default for small banks) executes the one-thread tracker's
+    operations in the same order on other lanes; every field of every call is the same, and equals the oracle's, on
+    noisy loop-back streams, silence (exact zeros: the -0 / +0 cases of the gathered sums), near silence, a stream that
+    goes dead mid-way, full-scale noise, and a bank size that leaves the last warp half empty."""
+    from helpers import compare_results, oracle_results
+    from singlecarrier_b200.modem import OPT_TRACKER, TRACKER_COOP, TRACKER_THREAD
+    rng = np.random.default_rng(4321)
+    ns, nf = 301, 12
+    samples = synth_streams(oracle, rng, ns, nf)
+    samples[7] = 0
+    samples[8, 5000:] = 0
+    samples[9] = (rng.integers(-3, 4, samples.shape[1])).astype(np.int16)
+    samples[10] = (rng.integers(-32768, 32768, samples.shape[1])).astype(np.int16)
+    out = {}
+    for mode in (TRACKER_THREAD, TRACKER_COOP):
+        bank = sc.ModemBank(ns)
+        bank.set_option(OPT_TRACKER, mode)
+        out[mode] = bank.rx_frames_host(samples, nf)
+        bank.close()
+    assert out[TRACKER_THREAD][0].tobytes() == out[TRACKER_COOP][0].tobytes()
+    obits, ostats = oracle_results(oracle, samples, nf)
+    assert compare_results(out[TRACKER_COOP][0], None, obits, ostats) == []
+    assert int(out[TRACKER_COOP][0]["valid"].sum()) > ns          # the locked branch of the data loop ran too
