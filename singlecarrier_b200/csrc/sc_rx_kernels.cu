@@ -414,76 +414,111 @@ track_kernel(const float2 *__restrict__ win, const int *__restrict__ max_index, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// track_coop_kernel: the same call, 16 lanes per stream (sc_tracker_coop.cuh) -- for banks too small to fill
-// the GPU with one thread per stream, where the tracker's dependent chain is the whole cost of a call.
+// track_coop_kernel: the same call, two warps per four streams (sc_tracker_coop.cuh) -- for banks too small
+// to fill the GPU with one thread per stream, where the tracker's dependent chain is the whole cost of a call.
 // ------------------------------------------------------------------------------------------------
 constexpr int TC_THREADS = 64;
+constexpr int TC_STREAMS = 32 / TC_LANES;                          // streams per CTA: one lane group each, per warp
+
+__device__ __forceinline__ void tc_barrier() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
 __global__ void __launch_bounds__(TC_THREADS)
 track_coop_kernel(const float2 *__restrict__ win, const int *__restrict__ max_index, const float *__restrict__ max_value,
                   const int *__restrict__ timing_cur, int *__restrict__ timing_next,
                   sc_frame_result *__restrict__ results, long result_stride, uint32_t call_index,
                   unsigned long long keystream, int n_streams) {
-    const int lane = threadIdx.x & 31;
-    const long s_raw = ((long) blockIdx.x * TC_THREADS + threadIdx.x) / TC_LANES;
-    const bool live = s_raw < n_streams;
-    const long s = live ? s_raw : n_streams - 1;                   // every lane stays in the shuffles
+    // The window is 198 rows of 8 bytes in L2 (the front-end has just written it), ~700 clocks away; a step is ~250.
+    // All of it is fetched at once into shared memory, then read from there.
+    __shared__ __align__(16) float2 s_win[TC_STREAMS][WIN_ROWS + 2];
+    __shared__ ExchangeA s_xa[2][TC_STREAMS];                      // what step k leaves for the taps: buffer k & 1
+    __shared__ ExchangeB s_xb[TC_STREAMS];
+    __shared__ int s_valid[TC_STREAMS];
 
-    CoopTracker tk;
-    tk.init(lane);
-    tk.reset();                                                    // qpsk.c:186
-
-    // The window is 198 rows of 8 bytes in L2 (the front-end has just written it), ~700 clocks away; a step is ~200.
-    // All of it is fetched at once into shared memory (13 loads in flight per lane), then read from there.
-    __shared__ float2 s_win[TC_THREADS / TC_LANES][WIN_ROWS + 2];
-    float2 *W = s_win[threadIdx.x / TC_LANES];
-    {
-        const float2 *X = win + ((s >> 5) * WIN_ROWS) * 32 + (s & 31);
-        const int g = lane & (TC_LANES - 1);
-#pragma unroll
-        for (int r = 0; r < (WIN_ROWS + TC_LANES - 1) / TC_LANES; r++) {
-            const int row = g + r * TC_LANES;
-            if (row < WIN_ROWS) W[row] = __ldg(X + row * 32);
-        }
+    const int lane = threadIdx.x & 31, g = lane & (TC_LANES - 1), qs = lane / TC_LANES;
+    const bool warp_a = threadIdx.x < 32;
+    if (warp_a) {
+        s_xa[0][qs].init(g);
+        s_xa[1][qs].init(g);
     }
-    __syncwarp();
-    const float2 *Xi = W + tk.myi, *Xj = W + tk.myj;
+    for (int q2 = 0; q2 < TC_STREAMS; q2++) {
+        const long s2 = min((long) blockIdx.x * TC_STREAMS + q2, (long) n_streams - 1);
+        const float2 *X = win + ((s2 >> 5) * WIN_ROWS) * 32 + (s2 & 31);
+        for (int row = threadIdx.x; row < WIN_ROWS; row += TC_THREADS) s_win[q2][row] = __ldg(X + row * 32);
+    }
+    __syncthreads();
+    const float2 *W = s_win[qs];
 
-    // equalize(), qpsk.c:111-123, and magnitude(), qpsk.c:101-109 (the sum over x[0] is kept by lanes with myi == 0)
+    if (warp_a) {
+        // ---- warp A: the gain recursion, one step ahead of the taps ----
+        KalmanColumn ka;
+        ka.init(lane);
+        ka.reset();                                                // qpsk.c:186
+        const float2 *X0 = W, *Xj = W + ka.myj;
+        c32 x[4];
+#pragma unroll 2
+        for (int k = 0; k < PRE; k++) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) x[i] = from2(X0[k + i]);
+            ka.step(x, from2(Xj[k]), &s_xa[k & 1][qs]);
+            tc_barrier();
+        }
+        tc_barrier();                                              // warp B has counted the matches of step 127
+        const int row0 = s_valid[qs] ? PRE : X_ROWS;               // qpsk.c:196
+        X0 += row0;
+        Xj += row0;
+#pragma unroll 1
+        for (int k = 0; k < NDATA; k++) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) x[i] = from2(X0[k + i]);
+            ka.step(x, from2(Xj[k]), &s_xa[k & 1][qs]);
+            tc_barrier();
+        }
+        return;
+    }
+
+    // ---- warp B: the taps ----
+    TapLanes tp;
+    tp.init(lane, &s_xb[qs]);
+    tp.reset();
+    const float2 *Xi = W + tp.i;
+
+    // equalize(), qpsk.c:111-123, and magnitude(), qpsk.c:101-109 (the sum over x[0] is the one lane 0 keeps)
     int matches = 0, bI, bQ;
     float mag = 0.0f;
-    c32 xi = from2(Xi[0]), xj = from2(Xj[0]);
+    c32 xi = from2(Xi[0]);
 #pragma unroll 2
     for (int k = 0; k < PRE; k++) {
-        const c32 ni = from2(Xi[k + 1]), nj = from2(Xj[k + 1]);
+        const c32 ni = from2(Xi[k + 1]);
         const float ref = ((c_pre_neg[k >> 5] >> (k & 31)) & 1u) ? -1.0f : 1.0f;
         mag = __fadd_rn(mag, __fadd_rn(__fmul_rn(xi.r, xi.r), __fmul_rn(xi.i, xi.i)));
-        const float er = tk.step<false>(xi, xj, ref, bI, bQ);
-        if (__fmul_rn(er, ref) > 0.0f) matches++;
+        const c32 err = tp.error<false>(xi, ref, bI, bQ);
+        if (__fmul_rn(err.r, ref) > 0.0f) matches++;
+        tc_barrier();
+        tp.update(err, &s_xa[k & 1][qs]);
         xi = ni;
-        xj = nj;
     }
     const bool valid = matches > MATCH_THRESHOLD;                  // qpsk.c:196
+    if (g == 0) s_valid[qs] = valid;
+    tc_barrier();
 
     // valid: data symbols follow the preamble; invalid: they start at rx_timing
-    const int row0 = valid ? PRE : X_ROWS;
-    Xi += row0;
-    Xj += row0;
+    Xi += valid ? PRE : X_ROWS;
     xi = from2(Xi[0]);
-    xj = from2(Xj[0]);
     unsigned long long word = 0ull;
     float cost = 0.0f;
 #pragma unroll 1
     for (int k = 0; k < NDATA; k++) {
-        const c32 ni = from2(Xi[k + 1]), nj = from2(Xj[k + 1]);    // at most row 197 + 1: inside the padded array
-        const float er = tk.step<true>(xi, xj, 0.0f, bI, bQ);
-        cost = __fadd_rn(cost, er);                                // qpsk.c:228
+        const c32 ni = from2(Xi[k + 1]);                           // at most row 197 + 1: inside the padded array
+        const c32 err = tp.error<true>(xi, 0.0f, bI, bQ);
+        cost = __fadd_rn(cost, err.r);                             // qpsk.c:228
         word |= ((unsigned long long) (unsigned) (bQ | (bI << 1))) << (2 * k);
+        tc_barrier();
+        tp.update(err, &s_xa[k & 1][qs]);
         xi = ni;
-        xj = nj;
     }
 
-    if (live && (lane & (TC_LANES - 1)) == 10) {                   // column lane 0: myi == 0, so mag is the real sum
+    const long s = (long) blockIdx.x * TC_STREAMS + qs;
+    if (g == 0 && s < n_streams) {
         TrackOut o;
         o.word = word;
         o.cost = valid ? mag : cost;
@@ -538,8 +573,7 @@ cudaError_t launch_track(bool debug_eq, const float2 *win, const int *max_index,
                          float *eq_dbg, float *state_dbg, uint32_t call_index, unsigned long long keystream,
                          int n_streams, cudaStream_t st, bool coop) {
     if (coop && !debug_eq) {
-        const long threads = (long) n_streams * TC_LANES;
-        track_coop_kernel<<<(int) ((threads + TC_THREADS - 1) / TC_THREADS), TC_THREADS, 0, st>>>(
+        track_coop_kernel<<<(n_streams + TC_STREAMS - 1) / TC_STREAMS, TC_THREADS, 0, st>>>(
             win, max_index, max_value, timing_cur, timing_next, results, result_stride, call_index, keystream, n_streams);
         g_launch_count++;
         return cudaGetLastError();
