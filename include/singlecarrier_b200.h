@@ -109,7 +109,17 @@ uint64_t sc_launch_count(void);
 #define SC_TRACKER_AUTO      0   /* cooperative up to SC_TRACKER_COOP_MAX streams per launch, else one thread each */
 #define SC_TRACKER_THREAD    1
 #define SC_TRACKER_COOP      2
-#define SC_TRACKER_COOP_MAX  8192
+#define SC_TRACKER_COOP_MAX  1024
+/* SC_OPT_OVERLAP: how the calls of a batch are queued.  Identical results either way.  A call's 128 training steps
+ * need only its symbol window; rx_timing (which the previous call may change) enters with the 31 data steps.  With
+ * the tracker cut there, the even and the odd calls of a batch form two chains that run side by side on two CUDA
+ * streams -- about twice the speed for a bank too small to fill the GPU, extra launches and traffic for a large one.
+ * AUTO: overlapped up to SC_OVERLAP_MAX streams per bank. */
+#define SC_OPT_OVERLAP       6
+#define SC_OVERLAP_AUTO      0
+#define SC_OVERLAP_OFF       1
+#define SC_OVERLAP_ON        2
+#define SC_OVERLAP_MAX       32768
 int  sc_set_option(sc_modem *m, int option, int64_t value);
 int  sc_profile_read(sc_modem *m, double out[4]);
 /* bytes queued host->device (out[0]) and device->host (out[1]) by sc_rx_frames_host since sc_create */

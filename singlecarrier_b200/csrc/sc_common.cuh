@@ -27,5 +27,7 @@ constexpr int MATCH_THRESHOLD = PRE - 30;     // qpsk.c:196: matches > 98
 constexpr int X_ROWS = PRE + NDATA + EQ - 1;  // 163
 constexpr int Y_ROWS = NDATA + EQ - 1;        // 35
 constexpr int WIN_ROWS = X_ROWS + Y_ROWS;     // 198
+constexpr int WIN_ROWS_OV = X_ROWS + (PRE - 1) + Y_ROWS;   // 325: overlapped chains keep W[128..289] instead of 35 chosen rows
+constexpr int TRK_STATE_WORDS = 64;           // floats per stream handed from the training to the data kernel
 
 }  // namespace sc

@@ -19,10 +19,17 @@ cudaError_t launch_nco_table(float2 *phase_state, float2 rect, int pattern, int 
 cudaError_t launch_frontend(bool wide, const int16_t *in, long stream_stride, const float2 *mix_table,
                             const int *timing_cur, const int *timing_next, float2 *win, int *max_index,
                             float *max_value, int n_streams, cudaStream_t st, const void *search_a_table = nullptr);
+// timing_next == nullptr: the tall window of the overlapped chains (WIN_ROWS_OV rows per tile, sc_common.cuh)
 cudaError_t launch_track(bool debug_eq, const float2 *win, const int *max_index, const float *max_value,
                          const int *timing_cur, int *timing_next, sc_frame_result *results, long result_stride,
                          float *eq_dbg, float *state_dbg, uint32_t call_index, unsigned long long keystream,
                          int n_streams, cudaStream_t st, bool coop = false);
+cudaError_t launch_track_train(const float2 *win_ov, float *state, long state_stride, int n_streams, cudaStream_t st,
+                               bool coop);
+cudaError_t launch_track_data(const float2 *win_ov, float *state, long state_stride, const int *max_index,
+                              const float *max_value, const int *timing_cur, int *timing_next, sc_frame_result *results,
+                              long result_stride, uint32_t call_index, unsigned long long keystream, int n_streams,
+                              cudaStream_t st, bool coop);
 constexpr int TRACK_STATE_FLOATS = 48;   // C[5], G[5], U[10] complex, D[5], KY, 2 pad: the drop-in shim's view
 
 // sc_stage_kernels.cu

@@ -156,12 +156,16 @@ __device__ __forceinline__ void fe_fir(const float2 *__restrict__ buf, int front
 // needed (rx_timing - 48) is never before the frame; it is clamped to keep a corrupt state in bounds.
 // MMA = true: the search is proposed on the tensor cores and verified exactly (sc_search_mma.cuh), one warp of
 // every warp PAIR doing it for both windows while the other goes on to the barrier; false: all 128 lags exact.
-template <bool WIDE, bool GENERIC, bool MMA>
+template <bool WIDE, bool GENERIC, bool MMA, bool OV>
 __global__ void __launch_bounds__(FE_WARPS * 32, 6)
 frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2 *__restrict__ mix_table,
                 const int *__restrict__ timing_cur, const int *__restrict__ timing_next,
                 float2 *__restrict__ win, int *__restrict__ max_index_out, float *__restrict__ max_value_out,
                 int n_streams, const uint4 *__restrict__ a_table) {
+    // OV = false: window rows 163.. are the 35 symbols from the NEXT call's rx_timing (the serial call chain);
+    // OV = true: rows 163.. are W[128 ..], every symbol an rx_timing of 128..255 can select, so that this kernel does
+    // not have to wait for the tracker of the call in between (overlapped chains, timing_next unused)
+    constexpr int win_rows = OV ? WIN_ROWS_OV : WIN_ROWS;
     __shared__ __align__(16) float2 smem[FE_WARPS][FE_BUF];
     __shared__ int s_maxidx[FE_WARPS];
     __shared__ int s_t2[FE_WARPS];
@@ -261,7 +265,7 @@ frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2
                 max_index_out[s] = best_idx;
                 max_value_out[s] = best_val;
                 s_maxidx[warp] = best_idx;
-                s_t2[warp] = timing_next[s];
+                s_t2[warp] = OV ? PRE : timing_next[s];
             }
         }
     } else {
@@ -328,7 +332,7 @@ frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2
                 max_index_out[s + lane] = idx;
                 max_value_out[s + lane] = lane ? bv[1] : bv[0];
                 s_maxidx[warp + lane] = idx;
-                s_t2[warp + lane] = timing_next[s + lane];
+                s_t2[warp + lane] = OV ? PRE : timing_next[s + lane];
             }
         }
     }
@@ -342,8 +346,8 @@ frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2
         if (sj < n_streams) {
             const int mi = s_maxidx[j], t2 = s_t2[j];
             const float2 *Wj = smem[j];
-            float2 *dst = win + ((sj >> 5) * WIN_ROWS) * 32 + (sj & 31);
-            for (int row = threadIdx.x / FE_WARPS; row < WIN_ROWS; row += (FE_WARPS * 32) / FE_WARPS) {
+            float2 *dst = win + ((sj >> 5) * win_rows) * 32 + (sj & 31);
+            for (int row = threadIdx.x / FE_WARPS; row < win_rows; row += (FE_WARPS * 32) / FE_WARPS) {
                 int src = row < X_ROWS ? mi + row : t2 + (row - X_ROWS);
                 float2 v = make_float2(0.f, 0.f);
                 if (src >= 0 && src < WIN) v = Wj[src];
@@ -363,6 +367,15 @@ struct TileLoader {
     __device__ __forceinline__ c32 x(int r) const { return from2(X[r * 32]); }
     __device__ __forceinline__ c32 y(int r) const { return from2(X[(X_ROWS + r) * 32]); }
 };
+
+// Overlapped chains: the window tile is WIN_ROWS_OV rows high, rows 163.. hold W[128 ..], and
+// the call's data symbols for the invalid branch start at row 163 + rx_timing - 128.
+struct TileLoaderOv {
+    const float2 *X, *Y;
+    __device__ __forceinline__ c32 x(int r) const { return from2(X[r * 32]); }
+    __device__ __forceinline__ c32 y(int r) const { return from2(Y[r * 32]); }
+};
+__device__ __forceinline__ int ov_alt_row(int rx_timing) { return X_ROWS + min(max(rx_timing - PRE, 0), PRE - 1); }
 
 template <bool DEBUG_EQ>
 __global__ void __launch_bounds__(TK_THREADS)
@@ -414,36 +427,121 @@ track_kernel(const float2 *__restrict__ win, const int *__restrict__ max_index, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// track_train_kernel / track_data_kernel: track_kernel cut at qpsk.c:196.  The 128 training steps need only the
+// window; rx_timing enters with the 31 data steps (the invalid branch reads from it, and the new rx_timing is either
+// max_index + 128 or the old one).  Cut there, the training of call n+1 no longer waits for call n, and two chains of
+// calls (even, odd) run side by side: what a bank too small to fill the GPU needs (sc_api.cu: run_slab_overlapped).
+// The tracker (eq_coeff, u, d), the match count and magnitude() travel through `state`, [TRK_STATE_WORDS][stride].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TK_THREADS)
+track_train_kernel(const float2 *__restrict__ win, float *__restrict__ state, long stride, int n_streams) {
+    const long s = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    TileLoaderOv ld;
+    ld.X = ld.Y = win + ((s >> 5) * WIN_ROWS_OV) * 32 + (s & 31);
+    Tracker tk;
+    int matches;
+    float mag;
+    track_train(ld, tk, matches, mag);
+    float *e = state + s;
+#pragma unroll
+    for (int i = 0; i < EQ; i++) {
+        e[(2 * i) * stride] = tk.C[i].r;
+        e[(2 * i + 1) * stride] = tk.C[i].i;
+        e[(30 + i) * stride] = tk.D[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        e[(10 + 2 * i) * stride] = tk.U[i].r;
+        e[(10 + 2 * i + 1) * stride] = tk.U[i].i;
+    }
+    e[35 * stride] = __int_as_float(matches);
+    e[36 * stride] = mag;
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+track_data_kernel(const float2 *__restrict__ win, const float *__restrict__ state, long stride,
+                  const int *__restrict__ max_index, const float *__restrict__ max_value,
+                  const int *__restrict__ timing_cur, int *__restrict__ timing_next, sc_frame_result *__restrict__ results,
+                  long result_stride, uint32_t call_index, unsigned long long keystream, int n_streams) {
+    const long s = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    const int t_in = timing_cur[s];
+    TileLoaderOv ld;
+    ld.X = win + ((s >> 5) * WIN_ROWS_OV) * 32 + (s & 31);
+    ld.Y = ld.X + ov_alt_row(t_in) * 32;
+    TrackOut o;
+    const float *e = state + s;
+#pragma unroll
+    for (int i = 0; i < EQ; i++) {
+        o.tk.C[i] = mk(e[(2 * i) * stride], e[(2 * i + 1) * stride]);
+        o.tk.D[i] = e[(30 + i) * stride];
+        o.tk.G[i] = mk(0.0f, 0.0f);                                 // G and KY are rebuilt by every step
+    }
+#pragma unroll
+    for (int i = 0; i < 10; i++) o.tk.U[i] = mk(e[(10 + 2 * i) * stride], e[(10 + 2 * i + 1) * stride]);
+    o.tk.KY = 0.0f;
+    o.matches = __float_as_int(e[35 * stride]);
+    const float mag = e[36 * stride];
+    o.valid = o.matches > MATCH_THRESHOLD;                          // qpsk.c:196
+    float cost;
+    track_data(ld, o.tk, o.valid, o.word, cost);
+    o.cost = o.valid ? mag : cost;
+
+    const int mi = max_index[s];
+    const int t_out = o.valid ? mi + PRE : t_in;                    // qpsk.c:219
+    timing_next[s] = t_out;
+    store_result(results + s * result_stride, o, keystream, max_value[s], mi, t_out, call_index);
+}
+
+// ------------------------------------------------------------------------------------------------
 // track_coop_kernel: the same call, two warps per four streams (sc_tracker_coop.cuh) -- for banks too small
 // to fill the GPU with one thread per stream, where the tracker's dependent chain is the whole cost of a call.
 // ------------------------------------------------------------------------------------------------
 constexpr int TC_THREADS = 64;
 constexpr int TC_STREAMS = 32 / TC_LANES;                          // streams per CTA: one lane group each, per warp
+enum { TRK_ALL = 0, TRK_TRAIN = 1, TRK_DATA = 2 };                 // the whole call, or one side of the cut at qpsk.c:196
+// what a cooperative TRK_TRAIN launch hands to its TRK_DATA launch, per stream (TRK_STATE_WORDS floats):
+//   [9 j + 2 i], [9 j + 2 i + 1] = U(i, j), [9 j + 8] = d[j]  (column lane j);  [45 + 2 i ..] = eq_coeff[i];
+//   [55] = matches, [56] = magnitude()
+static_assert(TRK_STATE_WORDS >= 57, "cooperative tracker state");
 
 __device__ __forceinline__ void tc_barrier() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
+template <int PHASE>
 __global__ void __launch_bounds__(TC_THREADS)
 track_coop_kernel(const float2 *__restrict__ win, const int *__restrict__ max_index, const float *__restrict__ max_value,
                   const int *__restrict__ timing_cur, int *__restrict__ timing_next,
                   sc_frame_result *__restrict__ results, long result_stride, uint32_t call_index,
-                  unsigned long long keystream, int n_streams) {
-    // The window is 198 rows of 8 bytes in L2 (the front-end has just written it), ~700 clocks away; a step is ~250.
+                  unsigned long long keystream, int n_streams, float *__restrict__ state) {
+    // The window is rows of 8 bytes in L2 (the front-end has just written it), ~700 clocks away; a step is ~250.
     // All of it is fetched at once into shared memory, then read from there.
-    __shared__ __align__(16) float2 s_win[TC_STREAMS][WIN_ROWS + 2];
+    constexpr int ROWS = PHASE == TRK_ALL ? WIN_ROWS : PHASE == TRK_TRAIN ? PRE + EQ : Y_ROWS + 1;
+    constexpr int TILE_ROWS = PHASE == TRK_ALL ? WIN_ROWS : WIN_ROWS_OV;
+    __shared__ __align__(16) float2 s_win[TC_STREAMS][ROWS + 2];
     __shared__ ExchangeA s_xa[2][TC_STREAMS];                      // what step k leaves for the taps: buffer k & 1
     __shared__ ExchangeB s_xb[TC_STREAMS];
     __shared__ int s_valid[TC_STREAMS];
 
     const int lane = threadIdx.x & 31, g = lane & (TC_LANES - 1), qs = lane / TC_LANES;
     const bool warp_a = threadIdx.x < 32;
+    const long s = min((long) blockIdx.x * TC_STREAMS + qs, (long) n_streams - 1);
+    const bool store = g == 0 && (long) blockIdx.x * TC_STREAMS + qs < n_streams;
+    float *st = state + s * TRK_STATE_WORDS;                       // PHASE != TRK_ALL only
     if (warp_a) {
         s_xa[0][qs].init(g);
         s_xa[1][qs].init(g);
     }
     for (int q2 = 0; q2 < TC_STREAMS; q2++) {
         const long s2 = min((long) blockIdx.x * TC_STREAMS + q2, (long) n_streams - 1);
-        const float2 *X = win + ((s2 >> 5) * WIN_ROWS) * 32 + (s2 & 31);
-        for (int row = threadIdx.x; row < WIN_ROWS; row += TC_THREADS) s_win[q2][row] = __ldg(X + row * 32);
+        const float2 *X = win + ((s2 >> 5) * TILE_ROWS) * 32 + (s2 & 31);
+        int first = 0;
+        if (PHASE == TRK_DATA) {
+            const bool v2 = __float_as_int(state[s2 * TRK_STATE_WORDS + 55]) > MATCH_THRESHOLD;
+            first = v2 ? PRE : ov_alt_row(timing_cur[s2]);
+        }
+        for (int row = threadIdx.x; row < ROWS; row += TC_THREADS)
+            s_win[q2][row] = __ldg(X + min(first + row, TILE_ROWS - 1) * 32);
     }
     __syncthreads();
     const float2 *W = s_win[qs];
@@ -452,20 +550,39 @@ track_coop_kernel(const float2 *__restrict__ win, const int *__restrict__ max_in
         // ---- warp A: the gain recursion, one step ahead of the taps ----
         KalmanColumn ka;
         ka.init(lane);
-        ka.reset();                                                // qpsk.c:186
         const float2 *X0 = W, *Xj = W + ka.myj;
         c32 x[4];
+        if (PHASE != TRK_DATA) {
+            ka.reset();                                            // qpsk.c:186
 #pragma unroll 2
-        for (int k = 0; k < PRE; k++) {
+            for (int k = 0; k < PRE; k++) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) x[i] = from2(X0[k + i]);
-            ka.step(x, from2(Xj[k]), &s_xa[k & 1][qs]);
-            tc_barrier();
+                for (int i = 0; i < 4; i++) x[i] = from2(X0[k + i]);
+                ka.step(x, from2(Xj[k]), &s_xa[k & 1][qs]);
+                tc_barrier();
+            }
         }
-        tc_barrier();                                              // warp B has counted the matches of step 127
-        const int row0 = s_valid[qs] ? PRE : X_ROWS;               // qpsk.c:196
-        X0 += row0;
-        Xj += row0;
+        if (PHASE == TRK_TRAIN) {
+            if (ka.live) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    st[9 * ka.myj + 2 * i] = ka.U[i].r;
+                    st[9 * ka.myj + 2 * i + 1] = ka.U[i].i;
+                }
+                st[9 * ka.myj + 8] = ka.D;
+            }
+            return;
+        }
+        if (PHASE == TRK_ALL) {
+            tc_barrier();                                          // warp B has counted the matches of step 127
+            const int row0 = s_valid[qs] ? PRE : X_ROWS;           // qpsk.c:196
+            X0 += row0;
+            Xj += row0;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) ka.U[i] = mk(st[9 * ka.myj + 2 * i], st[9 * ka.myj + 2 * i + 1]);
+            ka.D = st[9 * ka.myj + 8];
+        }
 #pragma unroll 1
         for (int k = 0; k < NDATA; k++) {
 #pragma unroll
@@ -479,36 +596,55 @@ track_coop_kernel(const float2 *__restrict__ win, const int *__restrict__ max_in
     // ---- warp B: the taps ----
     TapLanes tp;
     tp.init(lane, &s_xb[qs]);
-    tp.reset();
     const float2 *Xi = W + tp.i;
 
     // equalize(), qpsk.c:111-123, and magnitude(), qpsk.c:101-109 (the sum over x[0] is the one lane 0 keeps)
     int matches = 0, bI, bQ;
     float mag = 0.0f;
     c32 xi = from2(Xi[0]);
+    if (PHASE != TRK_DATA) {
+        tp.reset();
 #pragma unroll 2
-    for (int k = 0; k < PRE; k++) {
-        const c32 ni = from2(Xi[k + 1]);
-        const float ref = ((c_pre_neg[k >> 5] >> (k & 31)) & 1u) ? -1.0f : 1.0f;
-        mag = __fadd_rn(mag, __fadd_rn(__fmul_rn(xi.r, xi.r), __fmul_rn(xi.i, xi.i)));
-        const c32 err = tp.error<false>(xi, ref, bI, bQ);
-        if (__fmul_rn(err.r, ref) > 0.0f) matches++;
-        tc_barrier();
-        tp.update(err, &s_xa[k & 1][qs]);
-        xi = ni;
+        for (int k = 0; k < PRE; k++) {
+            const c32 ni = from2(Xi[k + 1]);
+            const float ref = ((c_pre_neg[k >> 5] >> (k & 31)) & 1u) ? -1.0f : 1.0f;
+            mag = __fadd_rn(mag, __fadd_rn(__fmul_rn(xi.r, xi.r), __fmul_rn(xi.i, xi.i)));
+            const c32 err = tp.error<false>(xi, ref, bI, bQ);
+            if (__fmul_rn(err.r, ref) > 0.0f) matches++;
+            tc_barrier();
+            tp.update(err, &s_xa[k & 1][qs]);
+            xi = ni;
+        }
+    }
+    if (PHASE == TRK_TRAIN) {
+        if (g < EQ) {
+            st[45 + 2 * tp.i] = tp.C.r;
+            st[45 + 2 * tp.i + 1] = tp.C.i;
+        }
+        if (g == 0) {
+            st[55] = __int_as_float(matches);
+            st[56] = mag;
+        }
+        return;
+    }
+    if (PHASE == TRK_DATA) {
+        tp.C = mk(st[45 + 2 * tp.i], st[45 + 2 * tp.i + 1]);
+        matches = __float_as_int(st[55]);
+        mag = st[56];
     }
     const bool valid = matches > MATCH_THRESHOLD;                  // qpsk.c:196
-    if (g == 0) s_valid[qs] = valid;
-    tc_barrier();
-
-    // valid: data symbols follow the preamble; invalid: they start at rx_timing
-    Xi += valid ? PRE : X_ROWS;
+    if (PHASE == TRK_ALL) {
+        if (g == 0) s_valid[qs] = valid;
+        tc_barrier();
+        // valid: data symbols follow the preamble; invalid: they start at rx_timing
+        Xi += valid ? PRE : X_ROWS;
+    }
     xi = from2(Xi[0]);
     unsigned long long word = 0ull;
     float cost = 0.0f;
 #pragma unroll 1
     for (int k = 0; k < NDATA; k++) {
-        const c32 ni = from2(Xi[k + 1]);                           // at most row 197 + 1: inside the padded array
+        const c32 ni = from2(Xi[k + 1]);                           // at most one row past the last: inside the padded array
         const c32 err = tp.error<true>(xi, 0.0f, bI, bQ);
         cost = __fadd_rn(cost, err.r);                             // qpsk.c:228
         word |= ((unsigned long long) (unsigned) (bQ | (bI << 1))) << (2 * k);
@@ -517,8 +653,7 @@ track_coop_kernel(const float2 *__restrict__ win, const int *__restrict__ max_in
         xi = ni;
     }
 
-    const long s = (long) blockIdx.x * TC_STREAMS + qs;
-    if (g == 0 && s < n_streams) {
+    if (store) {
         TrackOut o;
         o.word = word;
         o.cost = valid ? mag : cost;
@@ -551,17 +686,26 @@ cudaError_t launch_frontend(bool wide, const int16_t *in, long stream_stride, co
     // the fast kernel reads the samples as aligned 32-bit pairs: every frame must start on a 4-byte boundary
     const bool generic = ((((uintptr_t) in) & 3) != 0) || ((stream_stride & 1) != 0);
     const uint4 *at = (const uint4 *) search_a_table;
-#define SC_FE_LAUNCH(W, G, M)                                                                                      \
-    frontend_kernel<W, G, M><<<grid, thr, 0, st>>>(in, stream_stride, mix_table, timing_cur, timing_next, win, max_index, \
-                                                   max_value, n_streams, at)
-    if (wide) {
-        if (generic) SC_FE_LAUNCH(true, true, false);
-        else if (at) SC_FE_LAUNCH(true, false, true);
-        else SC_FE_LAUNCH(true, false, false);
+    const bool ov = timing_next == nullptr;                 // overlapped chains: the tall window, all-exact search only
+#define SC_FE_LAUNCH(W, G, M, O)                                                                                      \
+    frontend_kernel<W, G, M, O><<<grid, thr, 0, st>>>(in, stream_stride, mix_table, timing_cur, timing_next, win, max_index, \
+                                                      max_value, n_streams, at)
+    if (ov) {
+        if (wide) {
+            if (generic) SC_FE_LAUNCH(true, true, false, true);
+            else SC_FE_LAUNCH(true, false, false, true);
+        } else {
+            if (generic) SC_FE_LAUNCH(false, true, false, true);
+            else SC_FE_LAUNCH(false, false, false, true);
+        }
+    } else if (wide) {
+        if (generic) SC_FE_LAUNCH(true, true, false, false);
+        else if (at) SC_FE_LAUNCH(true, false, true, false);
+        else SC_FE_LAUNCH(true, false, false, false);
     } else {
-        if (generic) SC_FE_LAUNCH(false, true, false);
-        else if (at) SC_FE_LAUNCH(false, false, true);
-        else SC_FE_LAUNCH(false, false, false);
+        if (generic) SC_FE_LAUNCH(false, true, false, false);
+        else if (at) SC_FE_LAUNCH(false, false, true, false);
+        else SC_FE_LAUNCH(false, false, false, false);
     }
 #undef SC_FE_LAUNCH
     g_launch_count++;
@@ -573,8 +717,9 @@ cudaError_t launch_track(bool debug_eq, const float2 *win, const int *max_index,
                          float *eq_dbg, float *state_dbg, uint32_t call_index, unsigned long long keystream,
                          int n_streams, cudaStream_t st, bool coop) {
     if (coop && !debug_eq) {
-        track_coop_kernel<<<(n_streams + TC_STREAMS - 1) / TC_STREAMS, TC_THREADS, 0, st>>>(
-            win, max_index, max_value, timing_cur, timing_next, results, result_stride, call_index, keystream, n_streams);
+        track_coop_kernel<TRK_ALL><<<(n_streams + TC_STREAMS - 1) / TC_STREAMS, TC_THREADS, 0, st>>>(
+            win, max_index, max_value, timing_cur, timing_next, results, result_stride, call_index, keystream, n_streams,
+            nullptr);
         g_launch_count++;
         return cudaGetLastError();
     }
@@ -586,6 +731,36 @@ cudaError_t launch_track(bool debug_eq, const float2 *win, const int *max_index,
     else
         track_kernel<false><<<grid, thr, 0, st>>>(win, max_index, max_value, timing_cur, timing_next, results,
                                                          result_stride, eq_dbg, state_dbg, call_index, keystream, n_streams);
+    g_launch_count++;
+    return cudaGetLastError();
+}
+
+// The two halves of a call for the overlapped chains.  `state` is the slab's hand-over area: coop = false,
+// [TRK_STATE_WORDS][state_stride] with this slab's first stream at state[0]; coop = true, [n_streams][TRK_STATE_WORDS].
+cudaError_t launch_track_train(const float2 *win_ov, float *state, long state_stride, int n_streams, cudaStream_t st,
+                               bool coop) {
+    if (coop)
+        track_coop_kernel<TRK_TRAIN><<<(n_streams + TC_STREAMS - 1) / TC_STREAMS, TC_THREADS, 0, st>>>(
+            win_ov, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0u, 0ull, n_streams, state);
+    else
+        track_train_kernel<<<(n_streams + TK_THREADS - 1) / TK_THREADS, TK_THREADS, 0, st>>>(win_ov, state, state_stride,
+                                                                                            n_streams);
+    g_launch_count++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_track_data(const float2 *win_ov, float *state, long state_stride, const int *max_index,
+                              const float *max_value, const int *timing_cur, int *timing_next, sc_frame_result *results,
+                              long result_stride, uint32_t call_index, unsigned long long keystream, int n_streams,
+                              cudaStream_t st, bool coop) {
+    if (coop)
+        track_coop_kernel<TRK_DATA><<<(n_streams + TC_STREAMS - 1) / TC_STREAMS, TC_THREADS, 0, st>>>(
+            win_ov, max_index, max_value, timing_cur, timing_next, results, result_stride, call_index, keystream,
+            n_streams, state);
+    else
+        track_data_kernel<<<(n_streams + TK_THREADS - 1) / TK_THREADS, TK_THREADS, 0, st>>>(
+            win_ov, state, state_stride, max_index, max_value, timing_cur, timing_next, results, result_stride, call_index,
+            keystream, n_streams);
     g_launch_count++;
     return cudaGetLastError();
 }

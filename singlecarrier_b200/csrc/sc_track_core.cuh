@@ -22,16 +22,15 @@ struct TrackOut {
     Tracker tk;
 };
 
+// equalize(), qpsk.c:111-123, and magnitude(), qpsk.c:101-109, in one pass from a freshly reset tracker
 template <class Loader>
-__device__ __forceinline__ void track_core(const Loader &ld, TrackOut &o) {
-    Tracker &tk = o.tk;
+__device__ __forceinline__ void track_train(const Loader &ld, Tracker &tk, int &matches_out, float &mag_out) {
     tk.reset();                                                    // qpsk.c:186
 
     c32 x[EQ];
 #pragma unroll
     for (int i = 0; i < EQ - 1; i++) x[i] = ld.x(i);
 
-    // equalize(), qpsk.c:111-123, and magnitude(), qpsk.c:101-109, in one pass
     int matches = 0;
     float mag = 0.0f;
     c32 nxt = ld.x(EQ - 1);
@@ -48,13 +47,19 @@ __device__ __forceinline__ void track_core(const Loader &ld, TrackOut &o) {
 #pragma unroll
         for (int k = 0; k < EQ - 1; k++) x[k] = x[k + 1];
     }
+    matches_out = matches;
+    mag_out = mag;
+}
 
-    const bool valid = matches > MATCH_THRESHOLD;                  // qpsk.c:196
-
+// the 31 data_eq() steps of qpsk.c:206-215 (valid) / :226-229 (invalid), continuing from the trained tracker
+template <class Loader>
+__device__ __forceinline__ void track_data(const Loader &ld, Tracker &tk, bool valid, unsigned long long &word_out,
+                                           float &cost_out) {
     // valid: data symbols follow the preamble; invalid: they start at rx_timing
+    c32 x[EQ];
 #pragma unroll
     for (int i = 0; i < EQ - 1; i++) x[i] = valid ? ld.x(PRE + i) : ld.y(i);
-    nxt = valid ? ld.x(PRE + EQ - 1) : ld.y(EQ - 1);
+    c32 nxt = valid ? ld.x(PRE + EQ - 1) : ld.y(EQ - 1);
 
     unsigned long long word = 0ull;
     float cost = 0.0f;
@@ -70,7 +75,17 @@ __device__ __forceinline__ void track_core(const Loader &ld, TrackOut &o) {
 #pragma unroll
         for (int k = 0; k < EQ - 1; k++) x[k] = x[k + 1];
     }
-    o.word = word;
+    word_out = word;
+    cost_out = cost;
+}
+
+template <class Loader>
+__device__ __forceinline__ void track_core(const Loader &ld, TrackOut &o) {
+    int matches;
+    float mag, cost;
+    track_train(ld, o.tk, matches, mag);
+    const bool valid = matches > MATCH_THRESHOLD;                  // qpsk.c:196
+    track_data(ld, o.tk, valid, o.word, cost);
     o.cost = valid ? mag : cost;
     o.matches = matches;
     o.valid = valid;

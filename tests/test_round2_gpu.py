@@ -343,3 +343,59 @@ def test_lane_cooperative_tracker_is_bit_identical(sc, oracle):
     obits, ostats = oracle_results(oracle, samples, nf)
     assert compare_results(out[TRACKER_COOP][0], None, obits, ostats) == []
     assert int(out[TRACKER_COOP][0]["valid"].sum()) > ns          # the locked branch of the data loop ran too
+
+
+def test_overlapped_chains_are_bit_identical(sc, oracle):
+    """SC_OPT_OVERLAP: the tracker cut at qpsk.c:196 and the even / odd calls queued as two chains on two CUDA streams
+    (the default for small banks) give every field of every call as the serial call-by-call chain does and as the
+    oracle does -- with both trackers, from the host and the device entry point, for batches of 1, 2, 3 and many calls
+    (batches of one call cannot overlap and take the serial path, so the two modes also alternate on one handle), on
+    noisy loop-back streams, silence, a stream that goes dead, full-scale noise and a ragged last warp."""
+    import torch
+    from helpers import compare_results, oracle_results
+    from singlecarrier_b200.modem import (OPT_OVERLAP, OPT_TRACKER, OVERLAP_OFF, OVERLAP_ON, TRACKER_COOP,
+                                          TRACKER_THREAD)
+    rng = np.random.default_rng(97531)
+    ns, nf = 301, 14
+    samples = synth_streams(oracle, rng, ns, nf)
+    samples[7] = 0
+    samples[8, 5000:] = 0
+    samples[9] = (rng.integers(-3, 4, samples.shape[1])).astype(np.int16)
+    samples[10] = (rng.integers(-32768, 32768, samples.shape[1])).astype(np.int16)
+    obits, ostats = oracle_results(oracle, samples, nf)
+
+    bank = sc.ModemBank(ns)
+    bank.set_option(OPT_OVERLAP, OVERLAP_OFF)
+    serial = bank.rx_frames_host(samples, nf)
+    bank.close()
+    assert compare_results(serial[0], None, obits, ostats) == []
+    assert int(serial[0]["valid"].sum()) > ns
+
+    dev = torch.from_numpy(samples).cuda()
+    for tracker in (TRACKER_THREAD, TRACKER_COOP):
+        for splits in ([nf], [1, 2, 3, 1, 7], [2, 2, 2, 2, 2, 2, 2], [5, 9]):
+            bank = sc.ModemBank(ns)
+            bank.set_option(OPT_OVERLAP, OVERLAP_ON)
+            bank.set_option(OPT_TRACKER, tracker)
+            parts, f0 = [], 0
+            for k in splits:
+                parts.append(bank.rx_frames_host(samples[:, f0 * 1880:(f0 + k) * 1880], k)[0])
+                f0 += k
+            got = np.concatenate(parts, axis=1)
+            assert got.tobytes() == serial[0].tobytes(), (tracker, splits)
+            bank.close()
+        # device entry point, one batch and two
+        bank = sc.ModemBank(ns)
+        bank.set_option(OPT_OVERLAP, OVERLAP_ON)
+        bank.set_option(OPT_TRACKER, tracker)
+        res = torch.zeros((ns, nf * 32), dtype=torch.uint8, device="cuda")
+        bank.rx_frames_dev(dev, nf, res)
+        torch.cuda.synchronize()
+        assert res.cpu().numpy().tobytes() == serial[0].tobytes(), tracker
+        bank.reset()
+        res.zero_()
+        bank.rx_frames_dev(dev[:, :6 * 1880], 6, res[:, :6 * 32])
+        bank.rx_frames_dev(dev[:, 6 * 1880:], nf - 6, res[:, 6 * 32:])
+        torch.cuda.synchronize()
+        assert res.cpu().numpy().tobytes() == serial[0].tobytes(), tracker
+        bank.close()
