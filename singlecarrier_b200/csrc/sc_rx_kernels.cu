@@ -671,6 +671,45 @@ track_coop_kernel(const float2 *__restrict__ win, const int *__restrict__ max_in
 // host-side launchers (called from sc_api.cu)
 // ------------------------------------------------------------------------------------------------
 
+// Kernels of one call chain run side by side on different CUDA streams (two slabs; the even and the odd calls of a small
+// bank).  An SM only takes CTAs of kernels that agree on its shared-memory / L1 split, so the trackers (no or little
+// shared memory) are given the split the front-end needs (6 x 27 KB); without it a front-end launched while a tracker
+// kernel occupies every SM waits for that kernel to drain (measured: 50 us instead of 14 on a 1,024-stream bank).
+template <class K>
+static cudaError_t prefer_shared(K kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
+}
+static cudaError_t rx_kernel_attributes() {
+    static std::atomic<unsigned long long> done{0};            // bit per device
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && ((done.load() >> dev) & 1ull)) return cudaSuccess;
+#define SC_PREF(k)                          \
+    if ((e = prefer_shared(k)) != cudaSuccess) return e
+    SC_PREF((frontend_kernel<false, false, false, false>));
+    SC_PREF((frontend_kernel<false, true, false, false>));
+    SC_PREF((frontend_kernel<false, false, true, false>));
+    SC_PREF((frontend_kernel<true, false, false, false>));
+    SC_PREF((frontend_kernel<true, true, false, false>));
+    SC_PREF((frontend_kernel<true, false, true, false>));
+    SC_PREF((frontend_kernel<false, false, false, true>));
+    SC_PREF((frontend_kernel<false, true, false, true>));
+    SC_PREF((frontend_kernel<true, false, false, true>));
+    SC_PREF((frontend_kernel<true, true, false, true>));
+    SC_PREF(track_kernel<false>);
+    SC_PREF(track_kernel<true>);
+    SC_PREF(track_train_kernel);
+    SC_PREF(track_data_kernel);
+    SC_PREF(track_coop_kernel<TRK_ALL>);
+    SC_PREF(track_coop_kernel<TRK_TRAIN>);
+    SC_PREF(track_coop_kernel<TRK_DATA>);
+    SC_PREF(nco_table_kernel);
+#undef SC_PREF
+    if (dev < 64) done.fetch_or(1ull << dev);
+    return cudaSuccess;
+}
+
 cudaError_t launch_nco_table(float2 *phase_state, float2 rect, int pattern, int seg_single, int n_seg, float scale,
                              float2 *out, cudaStream_t st) {
     nco_table_kernel<<<1, 32, 0, st>>>(phase_state, rect, pattern, seg_single, n_seg, scale, out);
@@ -681,6 +720,8 @@ cudaError_t launch_nco_table(float2 *phase_state, float2 rect, int pattern, int 
 cudaError_t launch_frontend(bool wide, const int16_t *in, long stream_stride, const float2 *mix_table,
                             const int *timing_cur, const int *timing_next, float2 *win, int *max_index,
                             float *max_value, int n_streams, cudaStream_t st, const void *search_a_table) {
+    cudaError_t ea = rx_kernel_attributes();
+    if (ea != cudaSuccess) return ea;
     const int grid = (n_streams + FE_WARPS - 1) / FE_WARPS;
     const int thr = FE_WARPS * 32;
     // the fast kernel reads the samples as aligned 32-bit pairs: every frame must start on a 4-byte boundary
@@ -716,6 +757,8 @@ cudaError_t launch_track(bool debug_eq, const float2 *win, const int *max_index,
                          const int *timing_cur, int *timing_next, sc_frame_result *results, long result_stride,
                          float *eq_dbg, float *state_dbg, uint32_t call_index, unsigned long long keystream,
                          int n_streams, cudaStream_t st, bool coop) {
+    cudaError_t ea = rx_kernel_attributes();
+    if (ea != cudaSuccess) return ea;
     if (coop && !debug_eq) {
         track_coop_kernel<TRK_ALL><<<(n_streams + TC_STREAMS - 1) / TC_STREAMS, TC_THREADS, 0, st>>>(
             win, max_index, max_value, timing_cur, timing_next, results, result_stride, call_index, keystream, n_streams,
