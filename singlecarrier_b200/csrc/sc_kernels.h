@@ -12,14 +12,25 @@ namespace sc {
 
 extern std::atomic<unsigned long long> g_launch_count;
 
+// rx_timing at entry of call n where nobody has stored it yet: qpsk.c:219 applied to call n-1 by the reader.
+struct TimingSrc {
+    const float *matches = nullptr;   // call n-1's match count (int bits) at matches[s * mstride]; nullptr: T_n is stored
+    long mstride = 0;
+    const int *max_index = nullptr;   // the max_index call n-1 used
+    const int *timing_prev = nullptr; // T_{n-1}
+    int *timing_out = nullptr;        // where the reader leaves T_n (front-end only; may be nullptr)
+};
+
 // sc_rx_kernels.cu
 enum { NCO_RX = 0, NCO_TX_PACKET = 1, NCO_SINGLE = 2 };      // run lengths between phasor renormalisations
 cudaError_t launch_nco_table(float2 *phase_state, float2 rect, int pattern, int seg_single, int n_seg, float scale,
                              float2 *out, cudaStream_t st);
 cudaError_t launch_frontend(bool wide, const int16_t *in, long stream_stride, const float2 *mix_table,
                             const int *timing_cur, const int *timing_next, float2 *win, int *max_index,
-                            float *max_value, int n_streams, cudaStream_t st, const void *search_a_table = nullptr);
-// timing_next == nullptr: the tall window of the overlapped chains (WIN_ROWS_OV rows per tile, sc_common.cuh)
+                            float *max_value, int n_streams, cudaStream_t st, const void *search_a_table = nullptr,
+                            const TimingSrc *ts = nullptr);
+// timing_next == nullptr: the tall window of the overlapped chains (WIN_ROWS_OV rows per tile, sc_common.cuh); with
+// ts->matches set the kernel derives rx_timing itself instead of reading timing_cur
 cudaError_t launch_track(bool debug_eq, const float2 *win, const int *max_index, const float *max_value,
                          const int *timing_cur, int *timing_next, sc_frame_result *results, long result_stride,
                          float *eq_dbg, float *state_dbg, uint32_t call_index, unsigned long long keystream,
@@ -29,7 +40,8 @@ cudaError_t launch_track_train(const float2 *win_ov, float *state, long state_st
 cudaError_t launch_track_data(const float2 *win_ov, float *state, long state_stride, const int *max_index,
                               const float *max_value, const int *timing_cur, int *timing_next, sc_frame_result *results,
                               long result_stride, uint32_t call_index, unsigned long long keystream, int n_streams,
-                              cudaStream_t st, bool coop);
+                              cudaStream_t st, bool coop, const TimingSrc *ts = nullptr, int *timing_cur_out = nullptr);
+// timing_next / timing_cur_out may be nullptr (nothing stored)
 constexpr int TRACK_STATE_FLOATS = 48;   // C[5], G[5], U[10] complex, D[5], KY, 2 pad: the drop-in shim's view
 
 // sc_stage_kernels.cu

@@ -21,6 +21,13 @@
 
 namespace sc {
 
+// rx_timing at entry of a call: stored, or derived from the previous call's outcome (qpsk.c:196,219)
+__device__ __forceinline__ int resolve_timing(const TimingSrc &ts, const int *__restrict__ timing_cur, long s) {
+    if (ts.matches == nullptr) return timing_cur[s];
+    const bool valid = __float_as_int(ts.matches[s * ts.mstride]) > MATCH_THRESHOLD;
+    return valid ? ts.max_index[s] + PRE : ts.timing_prev[s];
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // NCO phasor table.  The reference advances one complex phasor per sample by a float recurrence
@@ -161,7 +168,7 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 6)
 frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2 *__restrict__ mix_table,
                 const int *__restrict__ timing_cur, const int *__restrict__ timing_next,
                 float2 *__restrict__ win, int *__restrict__ max_index_out, float *__restrict__ max_value_out,
-                int n_streams, const uint4 *__restrict__ a_table) {
+                int n_streams, const uint4 *__restrict__ a_table, TimingSrc ts) {
     // OV = false: window rows 163.. are the 35 symbols from the NEXT call's rx_timing (the serial call chain);
     // OV = true: rows 163.. are W[128 ..], every symbol an rx_timing of 128..255 can select, so that this kernel does
     // not have to wait for the tracker of the call in between (overlapped chains, timing_next unused)
@@ -188,7 +195,8 @@ frontend_kernel(const int16_t *__restrict__ in, long stream_stride, const float2
 #pragma unroll
     for (int k = 0; k < FE_KN; k++) raw[k] = 0u;
     if (active) {
-        const int T = timing_cur[s];
+        const int T = OV ? resolve_timing(ts, timing_cur, s) : timing_cur[s];
+        if (OV && ts.timing_out != nullptr && lane == 0) ts.timing_out[s] = T;
         base = max(min(T, 2 * PRE - 1) - (NTAPS - 1), 0);  // first sample needed: 80..207 for T in 128..255
         frame = in + s * stream_stride;
         if (!GENERIC) {
@@ -463,26 +471,44 @@ __global__ void __launch_bounds__(TK_THREADS)
 track_data_kernel(const float2 *__restrict__ win, const float *__restrict__ state, long stride,
                   const int *__restrict__ max_index, const float *__restrict__ max_value,
                   const int *__restrict__ timing_cur, int *__restrict__ timing_next, sc_frame_result *__restrict__ results,
-                  long result_stride, uint32_t call_index, unsigned long long keystream, int n_streams) {
+                  long result_stride, uint32_t call_index, unsigned long long keystream, int n_streams, TimingSrc ts,
+                  int *__restrict__ timing_cur_out, bool coop_state) {
     const long s = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_streams) return;
-    const int t_in = timing_cur[s];
+    const int t_in = resolve_timing(ts, timing_cur, s);
+    if (timing_cur_out != nullptr) timing_cur_out[s] = t_in;
     TileLoaderOv ld;
     ld.X = win + ((s >> 5) * WIN_ROWS_OV) * 32 + (s & 31);
     ld.Y = ld.X + ov_alt_row(t_in) * 32;
     TrackOut o;
-    const float *e = state + s;
+    float mag;
 #pragma unroll
-    for (int i = 0; i < EQ; i++) {
-        o.tk.C[i] = mk(e[(2 * i) * stride], e[(2 * i + 1) * stride]);
-        o.tk.D[i] = e[(30 + i) * stride];
-        o.tk.G[i] = mk(0.0f, 0.0f);                                 // G and KY are rebuilt by every step
-    }
-#pragma unroll
-    for (int i = 0; i < 10; i++) o.tk.U[i] = mk(e[(10 + 2 * i) * stride], e[(10 + 2 * i + 1) * stride]);
+    for (int i = 0; i < EQ; i++) o.tk.G[i] = mk(0.0f, 0.0f);       // G and KY are rebuilt by every step
     o.tk.KY = 0.0f;
-    o.matches = __float_as_int(e[35 * stride]);
-    const float mag = e[36 * stride];
+    if (coop_state) {
+        // left by track_coop_kernel<TRK_TRAIN>: [stream][TRK_STATE_WORDS], columns of u with their d, then eq_coeff
+        const float *e = state + s * TRK_STATE_WORDS;
+#pragma unroll
+        for (int j = 0; j < EQ; j++) {
+#pragma unroll
+            for (int i = 0; i < j; i++) o.tk.U[j * (j - 1) / 2 + i] = mk(e[9 * j + 2 * i], e[9 * j + 2 * i + 1]);
+            o.tk.D[j] = e[9 * j + 8];
+            o.tk.C[j] = mk(e[45 + 2 * j], e[45 + 2 * j + 1]);
+        }
+        o.matches = __float_as_int(e[55]);
+        mag = e[56];
+    } else {
+        const float *e = state + s;
+#pragma unroll
+        for (int i = 0; i < EQ; i++) {
+            o.tk.C[i] = mk(e[(2 * i) * stride], e[(2 * i + 1) * stride]);
+            o.tk.D[i] = e[(30 + i) * stride];
+        }
+#pragma unroll
+        for (int i = 0; i < 10; i++) o.tk.U[i] = mk(e[(10 + 2 * i) * stride], e[(10 + 2 * i + 1) * stride]);
+        o.matches = __float_as_int(e[35 * stride]);
+        mag = e[36 * stride];
+    }
     o.valid = o.matches > MATCH_THRESHOLD;                          // qpsk.c:196
     float cost;
     track_data(ld, o.tk, o.valid, o.word, cost);
@@ -490,7 +516,7 @@ track_data_kernel(const float2 *__restrict__ win, const float *__restrict__ stat
 
     const int mi = max_index[s];
     const int t_out = o.valid ? mi + PRE : t_in;                    // qpsk.c:219
-    timing_next[s] = t_out;
+    if (timing_next != nullptr) timing_next[s] = t_out;
     store_result(results + s * result_stride, o, keystream, max_value[s], mi, t_out, call_index);
 }
 
@@ -500,10 +526,11 @@ track_data_kernel(const float2 *__restrict__ win, const float *__restrict__ stat
 // ------------------------------------------------------------------------------------------------
 constexpr int TC_THREADS = 64;
 constexpr int TC_STREAMS = 32 / TC_LANES;                          // streams per CTA: one lane group each, per warp
-enum { TRK_ALL = 0, TRK_TRAIN = 1, TRK_DATA = 2 };                 // the whole call, or one side of the cut at qpsk.c:196
-// what a cooperative TRK_TRAIN launch hands to its TRK_DATA launch, per stream (TRK_STATE_WORDS floats):
+enum { TRK_ALL = 0, TRK_TRAIN = 1 };                               // the whole call, or the part before qpsk.c:196
+// what a cooperative TRK_TRAIN launch hands to track_data_kernel, per stream (TRK_STATE_WORDS floats):
 //   [9 j + 2 i], [9 j + 2 i + 1] = U(i, j), [9 j + 8] = d[j]  (column lane j);  [45 + 2 i ..] = eq_coeff[i];
 //   [55] = matches, [56] = magnitude()
+// (the 31 data steps of a cut call are off the chain's critical path and run one thread per stream: a 16th of the warps)
 static_assert(TRK_STATE_WORDS >= 57, "cooperative tracker state");
 
 __device__ __forceinline__ void tc_barrier() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
@@ -516,7 +543,7 @@ track_coop_kernel(const float2 *__restrict__ win, const int *__restrict__ max_in
                   unsigned long long keystream, int n_streams, float *__restrict__ state) {
     // The window is rows of 8 bytes in L2 (the front-end has just written it), ~700 clocks away; a step is ~250.
     // All of it is fetched at once into shared memory, then read from there.
-    constexpr int ROWS = PHASE == TRK_ALL ? WIN_ROWS : PHASE == TRK_TRAIN ? PRE + EQ : Y_ROWS + 1;
+    constexpr int ROWS = PHASE == TRK_ALL ? WIN_ROWS : PRE + EQ;
     constexpr int TILE_ROWS = PHASE == TRK_ALL ? WIN_ROWS : WIN_ROWS_OV;
     __shared__ __align__(16) float2 s_win[TC_STREAMS][ROWS + 2];
     __shared__ ExchangeA s_xa[2][TC_STREAMS];                      // what step k leaves for the taps: buffer k & 1
@@ -527,7 +554,7 @@ track_coop_kernel(const float2 *__restrict__ win, const int *__restrict__ max_in
     const bool warp_a = threadIdx.x < 32;
     const long s = min((long) blockIdx.x * TC_STREAMS + qs, (long) n_streams - 1);
     const bool store = g == 0 && (long) blockIdx.x * TC_STREAMS + qs < n_streams;
-    float *st = state + s * TRK_STATE_WORDS;                       // PHASE != TRK_ALL only
+    float *st = state + s * TRK_STATE_WORDS;                       // TRK_TRAIN only
     if (warp_a) {
         s_xa[0][qs].init(g);
         s_xa[1][qs].init(g);
@@ -535,13 +562,7 @@ track_coop_kernel(const float2 *__restrict__ win, const int *__restrict__ max_in
     for (int q2 = 0; q2 < TC_STREAMS; q2++) {
         const long s2 = min((long) blockIdx.x * TC_STREAMS + q2, (long) n_streams - 1);
         const float2 *X = win + ((s2 >> 5) * TILE_ROWS) * 32 + (s2 & 31);
-        int first = 0;
-        if (PHASE == TRK_DATA) {
-            const bool v2 = __float_as_int(state[s2 * TRK_STATE_WORDS + 55]) > MATCH_THRESHOLD;
-            first = v2 ? PRE : ov_alt_row(timing_cur[s2]);
-        }
-        for (int row = threadIdx.x; row < ROWS; row += TC_THREADS)
-            s_win[q2][row] = __ldg(X + min(first + row, TILE_ROWS - 1) * 32);
+        for (int row = threadIdx.x; row < ROWS; row += TC_THREADS) s_win[q2][row] = __ldg(X + row * 32);
     }
     __syncthreads();
     const float2 *W = s_win[qs];
@@ -550,17 +571,15 @@ track_coop_kernel(const float2 *__restrict__ win, const int *__restrict__ max_in
         // ---- warp A: the gain recursion, one step ahead of the taps ----
         KalmanColumn ka;
         ka.init(lane);
+        ka.reset();                                                // qpsk.c:186
         const float2 *X0 = W, *Xj = W + ka.myj;
         c32 x[4];
-        if (PHASE != TRK_DATA) {
-            ka.reset();                                            // qpsk.c:186
 #pragma unroll 2
-            for (int k = 0; k < PRE; k++) {
+        for (int k = 0; k < PRE; k++) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) x[i] = from2(X0[k + i]);
-                ka.step(x, from2(Xj[k]), &s_xa[k & 1][qs]);
-                tc_barrier();
-            }
+            for (int i = 0; i < 4; i++) x[i] = from2(X0[k + i]);
+            ka.step(x, from2(Xj[k]), &s_xa[k & 1][qs]);
+            tc_barrier();
         }
         if (PHASE == TRK_TRAIN) {
             if (ka.live) {
@@ -573,16 +592,10 @@ track_coop_kernel(const float2 *__restrict__ win, const int *__restrict__ max_in
             }
             return;
         }
-        if (PHASE == TRK_ALL) {
-            tc_barrier();                                          // warp B has counted the matches of step 127
-            const int row0 = s_valid[qs] ? PRE : X_ROWS;           // qpsk.c:196
-            X0 += row0;
-            Xj += row0;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; i++) ka.U[i] = mk(st[9 * ka.myj + 2 * i], st[9 * ka.myj + 2 * i + 1]);
-            ka.D = st[9 * ka.myj + 8];
-        }
+        tc_barrier();                                              // warp B has counted the matches of step 127
+        const int row0 = s_valid[qs] ? PRE : X_ROWS;               // qpsk.c:196
+        X0 += row0;
+        Xj += row0;
 #pragma unroll 1
         for (int k = 0; k < NDATA; k++) {
 #pragma unroll
@@ -596,25 +609,23 @@ track_coop_kernel(const float2 *__restrict__ win, const int *__restrict__ max_in
     // ---- warp B: the taps ----
     TapLanes tp;
     tp.init(lane, &s_xb[qs]);
+    tp.reset();
     const float2 *Xi = W + tp.i;
 
     // equalize(), qpsk.c:111-123, and magnitude(), qpsk.c:101-109 (the sum over x[0] is the one lane 0 keeps)
     int matches = 0, bI, bQ;
     float mag = 0.0f;
     c32 xi = from2(Xi[0]);
-    if (PHASE != TRK_DATA) {
-        tp.reset();
 #pragma unroll 2
-        for (int k = 0; k < PRE; k++) {
-            const c32 ni = from2(Xi[k + 1]);
-            const float ref = ((c_pre_neg[k >> 5] >> (k & 31)) & 1u) ? -1.0f : 1.0f;
-            mag = __fadd_rn(mag, __fadd_rn(__fmul_rn(xi.r, xi.r), __fmul_rn(xi.i, xi.i)));
-            const c32 err = tp.error<false>(xi, ref, bI, bQ);
-            if (__fmul_rn(err.r, ref) > 0.0f) matches++;
-            tc_barrier();
-            tp.update(err, &s_xa[k & 1][qs]);
-            xi = ni;
-        }
+    for (int k = 0; k < PRE; k++) {
+        const c32 ni = from2(Xi[k + 1]);
+        const float ref = ((c_pre_neg[k >> 5] >> (k & 31)) & 1u) ? -1.0f : 1.0f;
+        mag = __fadd_rn(mag, __fadd_rn(__fmul_rn(xi.r, xi.r), __fmul_rn(xi.i, xi.i)));
+        const c32 err = tp.error<false>(xi, ref, bI, bQ);
+        if (__fmul_rn(err.r, ref) > 0.0f) matches++;
+        tc_barrier();
+        tp.update(err, &s_xa[k & 1][qs]);
+        xi = ni;
     }
     if (PHASE == TRK_TRAIN) {
         if (g < EQ) {
@@ -627,24 +638,18 @@ track_coop_kernel(const float2 *__restrict__ win, const int *__restrict__ max_in
         }
         return;
     }
-    if (PHASE == TRK_DATA) {
-        tp.C = mk(st[45 + 2 * tp.i], st[45 + 2 * tp.i + 1]);
-        matches = __float_as_int(st[55]);
-        mag = st[56];
-    }
     const bool valid = matches > MATCH_THRESHOLD;                  // qpsk.c:196
-    if (PHASE == TRK_ALL) {
-        if (g == 0) s_valid[qs] = valid;
-        tc_barrier();
-        // valid: data symbols follow the preamble; invalid: they start at rx_timing
-        Xi += valid ? PRE : X_ROWS;
-    }
+    if (g == 0) s_valid[qs] = valid;
+    tc_barrier();
+
+    // valid: data symbols follow the preamble; invalid: they start at rx_timing
+    Xi += valid ? PRE : X_ROWS;
     xi = from2(Xi[0]);
     unsigned long long word = 0ull;
     float cost = 0.0f;
 #pragma unroll 1
     for (int k = 0; k < NDATA; k++) {
-        const c32 ni = from2(Xi[k + 1]);                           // at most one row past the last: inside the padded array
+        const c32 ni = from2(Xi[k + 1]);                           // at most row 197 + 1: inside the padded array
         const c32 err = tp.error<true>(xi, 0.0f, bI, bQ);
         cost = __fadd_rn(cost, err.r);                             // qpsk.c:228
         word |= ((unsigned long long) (unsigned) (bQ | (bI << 1))) << (2 * k);
@@ -671,10 +676,11 @@ track_coop_kernel(const float2 *__restrict__ win, const int *__restrict__ max_in
 // host-side launchers (called from sc_api.cu)
 // ------------------------------------------------------------------------------------------------
 
-// Kernels of one call chain run side by side on different CUDA streams (two slabs; the even and the odd calls of a small
-// bank).  An SM only takes CTAs of kernels that agree on its shared-memory / L1 split, so the trackers (no or little
-// shared memory) are given the split the front-end needs (6 x 27 KB); without it a front-end launched while a tracker
-// kernel occupies every SM waits for that kernel to drain (measured: 50 us instead of 14 on a 1,024-stream bank).
+// The kernels of the overlapped chains (a small bank's even and odd calls) run side by side on different CUDA streams.
+// An SM only takes CTAs of kernels that agree on its shared-memory / L1 split, so the cut trackers (little shared
+// memory) are given the split the front-end needs (6 x 27 KB); without it a front-end launched while a tracker kernel
+// occupies every SM waits for that kernel to drain (measured: 50 us instead of 14 on a 1,024-stream bank).  The
+// serial chain's kernels keep their defaults: on a bank that fills the GPU, co-residency costs 10 % (65,536 streams).
 template <class K>
 static cudaError_t prefer_shared(K kernel) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
@@ -687,24 +693,14 @@ static cudaError_t rx_kernel_attributes() {
     if (dev < 64 && ((done.load() >> dev) & 1ull)) return cudaSuccess;
 #define SC_PREF(k)                          \
     if ((e = prefer_shared(k)) != cudaSuccess) return e
-    SC_PREF((frontend_kernel<false, false, false, false>));
-    SC_PREF((frontend_kernel<false, true, false, false>));
-    SC_PREF((frontend_kernel<false, false, true, false>));
-    SC_PREF((frontend_kernel<true, false, false, false>));
-    SC_PREF((frontend_kernel<true, true, false, false>));
-    SC_PREF((frontend_kernel<true, false, true, false>));
     SC_PREF((frontend_kernel<false, false, false, true>));
     SC_PREF((frontend_kernel<false, true, false, true>));
     SC_PREF((frontend_kernel<true, false, false, true>));
     SC_PREF((frontend_kernel<true, true, false, true>));
-    SC_PREF(track_kernel<false>);
-    SC_PREF(track_kernel<true>);
     SC_PREF(track_train_kernel);
     SC_PREF(track_data_kernel);
     SC_PREF(track_coop_kernel<TRK_ALL>);
     SC_PREF(track_coop_kernel<TRK_TRAIN>);
-    SC_PREF(track_coop_kernel<TRK_DATA>);
-    SC_PREF(nco_table_kernel);
 #undef SC_PREF
     if (dev < 64) done.fetch_or(1ull << dev);
     return cudaSuccess;
@@ -719,7 +715,9 @@ cudaError_t launch_nco_table(float2 *phase_state, float2 rect, int pattern, int 
 
 cudaError_t launch_frontend(bool wide, const int16_t *in, long stream_stride, const float2 *mix_table,
                             const int *timing_cur, const int *timing_next, float2 *win, int *max_index,
-                            float *max_value, int n_streams, cudaStream_t st, const void *search_a_table) {
+                            float *max_value, int n_streams, cudaStream_t st, const void *search_a_table,
+                            const TimingSrc *tsp) {
+    const TimingSrc ts = tsp ? *tsp : TimingSrc();
     cudaError_t ea = rx_kernel_attributes();
     if (ea != cudaSuccess) return ea;
     const int grid = (n_streams + FE_WARPS - 1) / FE_WARPS;
@@ -730,7 +728,7 @@ cudaError_t launch_frontend(bool wide, const int16_t *in, long stream_stride, co
     const bool ov = timing_next == nullptr;                 // overlapped chains: the tall window, all-exact search only
 #define SC_FE_LAUNCH(W, G, M, O)                                                                                      \
     frontend_kernel<W, G, M, O><<<grid, thr, 0, st>>>(in, stream_stride, mix_table, timing_cur, timing_next, win, max_index, \
-                                                      max_value, n_streams, at)
+                                                      max_value, n_streams, at, ts)
     if (ov) {
         if (wide) {
             if (generic) SC_FE_LAUNCH(true, true, false, true);
@@ -779,7 +777,8 @@ cudaError_t launch_track(bool debug_eq, const float2 *win, const int *max_index,
 }
 
 // The two halves of a call for the overlapped chains.  `state` is the slab's hand-over area: coop = false,
-// [TRK_STATE_WORDS][state_stride] with this slab's first stream at state[0]; coop = true, [n_streams][TRK_STATE_WORDS].
+// [TRK_STATE_WORDS][state_stride] with this slab's first stream at state[0]; coop = true, [n_streams][TRK_STATE_WORDS]
+// (which kernel trained; the data steps always run one thread per stream).
 cudaError_t launch_track_train(const float2 *win_ov, float *state, long state_stride, int n_streams, cudaStream_t st,
                                bool coop) {
     if (coop)
@@ -795,15 +794,13 @@ cudaError_t launch_track_train(const float2 *win_ov, float *state, long state_st
 cudaError_t launch_track_data(const float2 *win_ov, float *state, long state_stride, const int *max_index,
                               const float *max_value, const int *timing_cur, int *timing_next, sc_frame_result *results,
                               long result_stride, uint32_t call_index, unsigned long long keystream, int n_streams,
-                              cudaStream_t st, bool coop) {
-    if (coop)
-        track_coop_kernel<TRK_DATA><<<(n_streams + TC_STREAMS - 1) / TC_STREAMS, TC_THREADS, 0, st>>>(
-            win_ov, max_index, max_value, timing_cur, timing_next, results, result_stride, call_index, keystream,
-            n_streams, state);
-    else
-        track_data_kernel<<<(n_streams + TK_THREADS - 1) / TK_THREADS, TK_THREADS, 0, st>>>(
-            win_ov, state, state_stride, max_index, max_value, timing_cur, timing_next, results, result_stride, call_index,
-            keystream, n_streams);
+                              cudaStream_t st, bool coop, const TimingSrc *tsp, int *timing_cur_out) {
+    const TimingSrc ts = tsp ? *tsp : TimingSrc();
+    // off the chains' critical path and sharing the SMs with their kernels: spread thin on small banks
+    const int thr = n_streams <= 148 * 32 ? 32 : n_streams <= 148 * 64 ? 64 : TK_THREADS;
+    track_data_kernel<<<(n_streams + thr - 1) / thr, thr, 0, st>>>(
+        win_ov, state, state_stride, max_index, max_value, timing_cur, timing_next, results, result_stride, call_index,
+        keystream, n_streams, ts, timing_cur_out, coop);
     g_launch_count++;
     return cudaGetLastError();
 }
