@@ -389,6 +389,11 @@ def main():
                          "ops_per_symbol": (FE_OPS + TK_OPS) / SYM_PER_FRAME,
                          "fp32_issue_frac": (value / world) * 1e6 * (FE_OPS + TK_OPS) / SYM_PER_FRAME / fp32_peak}
 
+    # ---- BASELINE.json configs[1]: a 1,024-stream bank, where a call is latency- and not throughput-bound ----------
+    small = None
+    if rank == 0 and world == 1:
+        small = run_small_bank(args, sc, torch, dev, n_frames)
+
     # ---- e2e: host buffers through sc_rx_frames_host ----------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -407,7 +412,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args),
-            "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_fast": cpu_fast, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_fast": cpu_fast, "e2e": e2e, "small_bank": small,
             "gpu_launches": int(launches), "clocks": clocks,
             "collective": ("sc_reduce_stats (ncclAllReduce of 16 uint64 through the C ABI), once per step" if comm is not None
                            else "none at N=1"),
@@ -422,6 +427,38 @@ def main():
         comm.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_small_bank(args, sc, torch, dev, n_frames, streams=1024):
+    """The same chain on a bank far too small to fill the GPU (BASELINE.json configs[1]), input resident in HBM: the
+    library's default for this size (the even and the odd calls as two overlapped chains, lane-cooperative training
+    kernel) beside the serial call-by-call chain the large bank uses.  Same results either way (tests)."""
+    from singlecarrier_b200.modem import OPT_OVERLAP, OPT_TRACKER, OVERLAP_OFF, TRACKER_THREAD
+    out = {"streams": streams, "unit": UNIT, "calls_per_step": n_frames,
+           "workload": "BASELINE.json configs[1]: 1,024 loop-back streams, random offset/phase, one bank on one GPU"}
+    res = torch.empty((streams, n_frames * 32), dtype=torch.uint8, device=dev)
+    for name, serial in (("value", False), ("serial_chain_value", True)):
+        bank = sc.ModemBank(streams, device=dev.index)
+        if serial:
+            bank.set_option(OPT_OVERLAP, OVERLAP_OFF)
+            bank.set_option(OPT_TRACKER, TRACKER_THREAD)
+        d_in = synth_input(sc, torch, bank, streams, args.seconds * 8000, args.seed + 1, 0)
+        for _ in range(3):
+            bank.reset()
+            bank.rx_frames_dev(d_in, n_frames, res)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            bank.reset()
+            bank.rx_frames_dev(d_in, n_frames, res)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 10
+        out[name] = streams * n_frames * SYM_PER_FRAME / (ms * 1e-3) / 1e6
+        out["us_per_call" if not serial else "serial_chain_us_per_call"] = 1e3 * ms / n_frames
+        bank.close()
+    return out
 
 
 def run_e2e(args, sc, torch, dist, bank, d_in, streams, n_frames, world, rank, dev, barrier):
