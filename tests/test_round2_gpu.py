@@ -399,3 +399,34 @@ def test_overlapped_chains_are_bit_identical(sc, oracle):
         torch.cuda.synchronize()
         assert res.cpu().numpy().tobytes() == serial[0].tobytes(), tracker
         bank.close()
+
+
+def test_overlapped_chains_many_slabs_and_blocks(sc, oracle):
+    """The overlapped chains with several slabs per pipe (host entry point: slabs of 4,096 streams round-robin on three
+    pipes, each with its own partner and data streams and its own region of the hand-over rings) and with two slabs on
+    the device entry point: byte-identical to the serial chain."""
+    import torch
+    from singlecarrier_b200.modem import OPT_OVERLAP, OVERLAP_OFF, OVERLAP_ON
+    rng = np.random.default_rng(2468)
+    nf = 7
+    base = synth_streams(oracle, rng, 150, nf)
+    ns = 17000
+    samples = np.empty((ns, base.shape[1]), np.int16)
+    for k in range(ns):                                            # shifted, scaled copies: cheap, all different
+        samples[k] = np.roll(base[k % 150], 37 * (k // 150)) // (1 + (k // 150) % 3)
+    out = {}
+    for mode in (OVERLAP_OFF, OVERLAP_ON):
+        bank = sc.ModemBank(ns)
+        bank.set_option(OPT_OVERLAP, mode)
+        a = bank.rx_frames_host(samples[:, :3 * 1880], 3)[0]
+        b = bank.rx_frames_host(samples[:, 3 * 1880:], nf - 3)[0]
+        bank.reset()
+        dev = torch.from_numpy(samples).cuda()
+        res = torch.zeros((ns, nf * 32), dtype=torch.uint8, device="cuda")
+        bank.rx_frames_dev(dev, nf, res)
+        torch.cuda.synchronize()
+        out[mode] = (np.concatenate([a, b], axis=1).tobytes(), res.cpu().numpy().tobytes())
+        bank.close()
+    assert out[OVERLAP_ON][0] == out[OVERLAP_OFF][0]
+    assert out[OVERLAP_ON][1] == out[OVERLAP_OFF][1]
+    assert out[OVERLAP_ON][0] == out[OVERLAP_ON][1]
