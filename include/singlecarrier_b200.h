@@ -261,6 +261,15 @@ int sc_fir_batch_dev(int device, int64_t n_streams, int wide, float *memory, flo
 int sc_preamble_search_batch_dev(int device, int64_t n_streams, const float *symbols,
                                  int64_t symbol_stride, int32_t *max_index, float *max_value,
                                  void *stream);
+/* the two tensor-core forms by name: mma.sync (any window layout) and tcgen05 + tensor memory + TMA (symbol_stride
+ * >= 256 and even, array 16-byte aligned; approx, optional, receives the proposed |correlation|^2 [n_streams][128]).
+ * sc_preamble_search_batch_dev picks tcgen05 when the layout allows it. */
+int sc_preamble_search_mma_batch_dev(int device, int64_t n_streams, const float *symbols,
+                                     int64_t symbol_stride, int32_t *max_index, float *max_value,
+                                     void *stream);
+int sc_preamble_search_tcgen05_batch_dev(int device, int64_t n_streams, const float *symbols,
+                                         int64_t symbol_stride, int32_t *max_index, float *max_value,
+                                         float *approx, void *stream);
 int sc_preamble_search_fft_batch_dev(int device, int64_t n_streams, const float *symbols,
                                      int64_t symbol_stride, int32_t *max_index, float *max_value,
                                      void *stream);

@@ -64,6 +64,8 @@ def _load() -> C.CDLL:
     sig("sc_preamble_search_batch_dev", i32, i32, i64, vp, i64, vp, vp, vp)
     sig("sc_preamble_search_direct_batch_dev", i32, i32, i64, vp, i64, vp, vp, vp)
     sig("sc_preamble_search_fft_batch_dev", i32, i32, i64, vp, i64, vp, vp, vp)
+    sig("sc_preamble_search_mma_batch_dev", i32, i32, i64, vp, i64, vp, vp, vp)
+    sig("sc_preamble_search_tcgen05_batch_dev", i32, i32, i64, vp, i64, vp, vp, vp, vp)
     sig("sc_track_decide_batch_dev", i32, i32, i64, vp, i64, vp, vp, vp, u32, vp, vp, vp)
     sig("sc_fft_batch_dev", i32, i32, i64, i32, i32, vp, vp, vp)
     sig("sc_fftr_batch_dev", i32, i32, i64, i32, vp, vp, vp)
