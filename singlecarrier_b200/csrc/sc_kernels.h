@@ -56,11 +56,8 @@ void search_fft_make_table(float *table /* [8][32][2] */);
 cudaError_t launch_search_fft_batch(long n_streams, const float2 *symbols, long symbol_stride, const float2 *tw,
                                     const void *ptab, int *max_index, float *max_value, cudaStream_t st);
 // sc_search_umma.cu: the same search with the proposer on tcgen05 / tensor memory and TMA bulk loads
-constexpr int SU_A_ROWS = 368;                       // master rows r = -240 .. 127 of M[r][k] = pre[k - r]
-constexpr int SU_A_WORDS4 = 2 * ((SU_A_ROWS + 7) / 8) * 128 / 16;   // 16-byte words of the master (11,776 bytes)
-void search_umma_make_master(uint16_t *table /* [SU_A_WORDS4 * 8] */);
 bool search_umma_eligible(const float2 *symbols, long symbol_stride);
-cudaError_t launch_search_umma_batch(long n_streams, const float2 *symbols, long symbol_stride, const void *a_master,
+cudaError_t launch_search_umma_batch(long n_streams, const float2 *symbols, long symbol_stride,
                                      int *max_index, float *max_value, float *dbg_approx, cudaStream_t st);
 cudaError_t launch_track_window_batch(long n_streams, const float2 *symbols, long symbol_stride,
                                       const int *max_index, const float *max_value, int *rx_timing,

@@ -241,14 +241,15 @@ def test_reduce_stats_through_the_c_abi(sc, oracle):
 
 
 def test_tensor_core_proposed_search_equals_direct_search(sc, oracle):
-    """sc_preamble_search_batch_dev (tensor-core proposer + exact verifier) against the all-exact kernel, bit for
+    """sc_preamble_search_batch_dev (tensor-core proposer + exact verifier: tcgen05 + tensor memory + TMA where the
+    window layout allows it, mma.sync otherwise; both also by name) against the all-exact kernel, bit for
     bit, on 200k windows built to stress the candidate logic: noise only, planted preambles at every lag, several
     equal maxima (ties), silence, one non-zero symbol, tiny and huge amplitudes, a window repeated with a one-ulp
     change, and odd window counts / strides."""
     import torch
     pv = np.frombuffer((C.c_int8 * 128).in_dll(oracle.lib, "sco_preamblevalues"), np.int8).astype(np.float32)
     rng = np.random.default_rng(42)
-    for ns, stride in ((200001, 255), (777, 260)):
+    for ns, stride in ((200001, 255), (777, 260), (200003, 256)):
         sym = (rng.normal(size=(ns, stride)) + 1j * rng.normal(size=(ns, stride))).astype(np.complex64)
         k = min(ns - 500, 4000)
         for s in range(0, k):                                   # planted preambles, every lag, various SNR
@@ -269,12 +270,22 @@ def test_tensor_core_proposed_search_equals_direct_search(sc, oracle):
         sym[k + 350:k + 400, 77] = np.nextafter(sym[k + 400:k + 450, 77].real, np.float32(9)) + 1j * sym[k + 400:k + 450, 77].imag
         d = torch.from_numpy(sym.view(np.float32)).cuda()
         out = {}
-        for name in ("sc_preamble_search_batch_dev", "sc_preamble_search_fft_batch_dev", "sc_preamble_search_direct_batch_dev"):
+        names = ["sc_preamble_search_batch_dev", "sc_preamble_search_fft_batch_dev", "sc_preamble_search_direct_batch_dev",
+                 "sc_preamble_search_mma_batch_dev"]
+        if stride >= 256 and stride % 2 == 0:                   # the layout the tcgen05 / TMA kernel takes
+            names.append("sc_preamble_search_tcgen05_batch_dev")
+        for name in names:
             idx = torch.full((ns,), -7, dtype=torch.int32, device="cuda")
             val = torch.full((ns,), -7.0, dtype=torch.float32, device="cuda")
-            sc._lib.check(getattr(sc.lib, name)(0, ns, d.data_ptr(), stride, idx.data_ptr(), val.data_ptr(), 0))
+            args = (0, ns, d.data_ptr(), stride, idx.data_ptr(), val.data_ptr())
+            sc._lib.check(getattr(sc.lib, name)(*args, None, 0) if "tcgen05" in name else getattr(sc.lib, name)(*args, 0))
             torch.cuda.synchronize()
             out[name] = (idx.cpu().numpy(), val.cpu().numpy())
+        for name in names:
+            xi, xv = out[name]
+            yi, yv = out["sc_preamble_search_direct_batch_dev"]
+            bad = np.nonzero((xi != yi) | (xv.view(np.uint32) != yv.view(np.uint32)))[0]
+            assert bad.size == 0, (name, bad[:10], xi[bad[:10]], yi[bad[:10]], xv[bad[:10]], yv[bad[:10]])
         (ai, av), (bi, bv) = out["sc_preamble_search_batch_dev"], out["sc_preamble_search_direct_batch_dev"]
         bad = np.nonzero((ai != bi) | (av.view(np.uint32) != bv.view(np.uint32)))[0]
         assert bad.size == 0, (bad[:10], ai[bad[:10]], bi[bad[:10]], av[bad[:10]], bv[bad[:10]])

@@ -79,3 +79,18 @@ def test_compiled_for_sm_100a_only():
     out = subprocess.run([exe, "-lelf", LIB], check=True, capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))
     assert archs == {"sm_100a"}, archs
+
+
+def test_tcgen05_search_kernel_uses_the_blackwell_units():
+    """search_umma_batch_kernel (sc_search_umma.cu): the proposer's GEMM is tcgen05.mma with A and D in tensor memory
+    (UTCHMMA, LDTM / STTM, the allocator's UTCATOMSWS), its completion a tcgen05.commit on an mbarrier (UTCBAR), the
+    windows arrive by TMA bulk copies (UBLKCP) -- and the verifier's sums contain no multiply-add."""
+    funcs = sass()
+    names = [n for n in funcs if "search_umma_batch_kernel" in n]
+    assert len(names) == 1, names
+    ins = funcs[names[0]]
+    for mnem, least in (("UTCHMMA", 1), ("LDTM", 4), ("STTM", 1), ("UTCBAR", 1), ("UBLKCP", 1), ("UTCATOMSWS", 2),
+                        ("SYNCS", 6), ("REDUX", 16), ("LDGSTS", 33)):
+        assert sum(mnem in i for i in ins) >= least, (mnem, sum(mnem in i for i in ins))
+    assert not [i for i in ins if "FFMA" in i or "HMMA.16816" in i]
+    assert sum(bool(re.match(r"(@!?P\d+\s+)?FADD\b", i)) for i in ins) >= 256

@@ -47,9 +47,25 @@ ns = 1 << 20
 s = torch.randn((ns, 256, 2), device="cuda")
 idx = torch.empty(ns, dtype=torch.int32, device="cuda")
 val = torch.empty(ns, dtype=torch.float32, device="cuda")
-ms = timeit(lambda: check(L.sc_preamble_search_batch_dev(0, ns, s.data_ptr(), 256, idx.data_ptr(), val.data_ptr(), None)))
+ms = timeit(lambda: check(L.sc_preamble_search_tcgen05_batch_dev(0, ns, s.data_ptr(), 256, idx.data_ptr(), val.data_ptr(), None, None)))
 gbs = ns * 2048 / ms / 1e6
-rows.append(("search_mma_batch_kernel (tensor-core proposer + exact verifier)", f"{ns} windows", ms, gbs, gbs / peak, "-"))
+rows.append(("search_umma_batch_kernel (tcgen05 + TMEM + TMA proposer, exact verifier), noise-only windows", f"{ns} windows", ms, gbs, gbs / peak, "-"))
+# the same with a preamble in every window (one clear maximum: a single candidate per window)
+import ctypes as C
+import numpy as np
+pre = torch.from_numpy(np.frombuffer((C.c_int8 * 128).in_dll(L, "preamblevalues"), np.int8).astype(np.float32)).cuda()
+s2 = s.clone()
+lag = (torch.arange(ns, device="cuda") * 37) % 128
+cols = lag[:, None] + torch.arange(128, device="cuda")[None, :]
+s2.scatter_add_(1, cols[:, :, None].expand(-1, -1, 2), (3.0 * pre)[None, :, None].expand(ns, -1, 2).contiguous())
+ms = timeit(lambda: check(L.sc_preamble_search_tcgen05_batch_dev(0, ns, s2.data_ptr(), 256, idx.data_ptr(), val.data_ptr(), None, None)))
+gbs = ns * 2048 / ms / 1e6
+rows.append(("search_umma_batch_kernel, a preamble in every window", f"{ns} windows", ms, gbs, gbs / peak, "-"))
+assert bool((idx.long() == lag).float().mean() > 0.999)
+del s2, cols
+ms = timeit(lambda: check(L.sc_preamble_search_mma_batch_dev(0, ns, s.data_ptr(), 256, idx.data_ptr(), val.data_ptr(), None)))
+gbs = ns * 2048 / ms / 1e6
+rows.append(("search_mma_batch_kernel (mma.sync proposer + exact verifier)", f"{ns} windows", ms, gbs, gbs / peak, "-"))
 ms = timeit(lambda: check(L.sc_preamble_search_fft_batch_dev(0, ns, s.data_ptr(), 256, idx.data_ptr(), val.data_ptr(), None)))
 gbs = ns * 2048 / ms / 1e6
 rows.append(("search_fft_batch_kernel (warp-shuffle FFT proposer + exact verifier)", f"{ns} windows", ms, gbs, gbs / peak, "-"))
