@@ -8,7 +8,10 @@ python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null > gpurun_out/bench_ref_$R.json
 python bench.py 2>gpurun_out/bench.err > gpurun_out/bench_$R.json
-python tools/stage_bench.py 2>&1 | tail -10 > gpurun_out/stage_bench_$R.md
+python tools/stage_bench.py 2>&1 | tail -14 > gpurun_out/stage_bench_$R.md
+python tools/small_bank_bench.py 512 1024 2048 4096 8192 16384 32768 65536 > gpurun_out/small_bank_$R.md 2>&1
+python tools/umma_bench.py > gpurun_out/umma_bench_$R.txt 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'search_umma_batch_kernel|search_mma_batch_kernel' -s 8 -c 2 -o gpurun_out/prof_search_$R python tools/umma_bench.py > gpurun_out/ncu_search.log 2>&1
 # launch list (every launch with its device time; compare shares)
 CMD="python bench.py --streams 131072 --seconds 2 --steps 2 --warmup 3 --no-e2e --no-cpu"
 $CMD > gpurun_out/plain_$R.log 2>&1 &&
