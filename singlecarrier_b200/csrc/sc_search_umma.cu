@@ -583,11 +583,20 @@ search_umma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride,
             for (int k = 0; k < rounds; k++) {
                 const bool have = direct && k < nc;
                 const int L = have ? kth(k) : 0;
-                if (have) gather(scr, L);
-                asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-                __syncwarp();
-                if (have) take(scr, L);
-                __syncwarp();
+                {
+                    SU_T0
+                    if (have) gather(scr, L);
+                    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                    SU_T1(w1)
+                }
+                {
+                    SU_T0
+                    if (have) take(scr, L);
+                    __syncwarp();
+                    SU_T1(w2)
+                }
+                w3 += 1;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh.cand_empty[slot]);           // the lists have been read: the slot is free

@@ -11,7 +11,7 @@ dbg = torch.zeros((ns, 128), dtype=torch.float32, device="cuda")
 for _ in range(2):
     sc._lib.check(sc.lib.sc_preamble_search_tcgen05_batch_dev(0, ns, d.data_ptr(), stride, idx.data_ptr(), val.data_ptr(), dbg.data_ptr(), 0))
 torch.cuda.synchronize()
-o = dbg.view(-1)[:8 * 24].cpu().numpy().reshape(-1, 8)
-names = [f"epi{i}" for i in range(8)] + ["mma0", "mma1", "tma"] + [f"stg{i}" for i in range(8)] + [f"ver{i}" for i in range(5)]
+o = dbg.view(-1)[:8 * 22].cpu().numpy().reshape(-1, 8)
+names = [f"epi{i}" for i in range(8)] + ["mma0", "mma1", "tma"] + [f"stg{i}" for i in range(8)] + [f"ver{i}" for i in range(3)]
 for n, r in zip(names, o):
     print(f"{n:5s} total {r[0]:10.0f} " + " ".join(f"w{k} {100*r[k+1]/r[0]:5.1f}%" for k in range(6)))
