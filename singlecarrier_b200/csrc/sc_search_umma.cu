@@ -20,15 +20,16 @@
 //       2 x 4 epilogue  thread = lag: tcgen05.ld of its 64 accumulators, |re|^2 + |im|^2 for the 16 windows, redux.sync
 //         warps         maxima, the bound's threshold, candidate lists by ballot;
 //       3 verify warps  lane = (window, component): the candidate's 128 symbols L2 -> shared memory by cp.async, the
-//                       reference's 128 sequential adds, the reference's argmax rule; the rare fallbacks (no or too
-//                       many candidates) run the full exact search;
+//                       reference's 128 sequential adds, the reference's argmax rule; second candidates are queued
+//                       and verified 16 at a time; the rare fallbacks (no or too many candidates) run the full
+//                       exact search;
 //   * the A operand P (+-1 / 0) is written into tensor memory once per CTA (thread = lag = row, 128 columns of bf16
 //     pairs) and read from there by every MMA: the shared-memory pipe then only feeds B (2 KB per MMA).  (First form:
 //     A from shared memory through a descriptor -- slice s of the Toeplitz matrix is a 368 x 16 master read from row
 //     240 - 16 s on, so 11.5 KB served all 16 slices -- correct, but slower.)
 //
-// Measured (tools/umma_bench.py, 2^20 windows): 0.57 ms with a preamble in every window, 0.68 ms on noise-only windows
-// (4 % of which have a second candidate) -- 58 % / 49 % of the measured HBM peak, against 0.99 ms for the mma.sync
+// Measured (tools/umma_bench.py, 2^20 windows): 0.59 ms with a preamble in every window, 0.64 ms on noise-only windows
+// (4 % of which have a second candidate) -- 56 % / 52 % of the measured HBM peak, against 0.99 ms for the mma.sync
 // kernel (shared-memory pipe at 85 %) and 1.45 ms for the all-exact one.  What bounds it now is spread over the roles
 // (make SU_DEFS=-DSU_PROFILE + tools/umma_prof.py shows where each waits): every role is one warp per scheduler
 // running dependent code.
@@ -86,6 +87,7 @@ struct SuShared {
     uint32_t warp_max[2][SU_EPI_WARPS][SU_WIN];      // per epilogue set
     float part_abs[4][SU_STG_WARPS][SU_WIN];         // sum(|d| + |e|) per staging warp and window, slot n % 4
     // candidates of window w among the 32 lags of epilogue warp q: count (may exceed the list) and the first 8 lags
+    int2 defer[SU_SLOTS][SU_WIN];                    // per verify warp: postponed second candidates (window, lag)
     int n_cand[SU_LISTS][SU_EPI_WARPS][SU_WIN];
     unsigned char cand[SU_LISTS][SU_EPI_WARPS][SU_WIN][SM_MAX_CAND];
 };
@@ -275,6 +277,40 @@ __device__ __forceinline__ void su_search_warp(const float2 *__restrict__ W, int
         }
     }
     if (!(best_val > 0.0f)) best_idx = 0;
+}
+
+// One verify round over a warp's queue of postponed second candidates (see the verify role below): gather, exact
+// sums, and the window's stored result corrected in place.  Kept out of line: it runs once in ~20 batches and would
+// otherwise double the verify role's code.
+__device__ __noinline__ void su_flush_queue(const int2 *__restrict__ queue, int qn, float2 *__restrict__ scr,
+                                            const float2 *__restrict__ symbols, long symbol_stride,
+                                            int *__restrict__ max_index, float *__restrict__ max_value, int lane) {
+    const int w = lane >> 1, comp = lane & 1;
+    const bool have = w < qn;
+    const int2 it = have ? queue[w] : make_int2(0, 0);
+    if (have) {
+        const float2 *src = symbols + (long) it.x * symbol_stride + (it.y & ~1);
+#pragma unroll
+        for (int i = 0; i < 33; i++) {
+            const int ch = 2 * i + comp;
+            if (ch < 65) cp_async16(scr + 2 * ch, src + 2 * ch);
+        }
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    if (have) {
+        const float part = su_exact_sum(scr + (it.y & 1), comp);
+        const float sq = __fmul_rn(part, part);
+        const float v = __fadd_rn(sq, __shfl_xor_sync(0x3u << (lane & ~1), sq, 1));   // cnormf, qpsk.c:75-80
+        if (comp == 0) {                                        // strict '>' scanning the lags upwards: larger wins, and
+            const float cur = max_value[it.x];                  // among equals the lower lag
+            if (v > cur || (v == cur && v > 0.0f && it.y < max_index[it.x])) {
+                max_value[it.x] = v;
+                max_index[it.x] = it.y;
+            }
+        }
+    }
+    __syncwarp();
 }
 
 __device__ __forceinline__ void epi_bar(int set) {                     // the 128 threads of one epilogue set
@@ -530,6 +566,31 @@ search_umma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride,
         const int vw = warp - SU_VER_WARP0;
         const int w = lane >> 1, comp = lane & 1;
         float2 *scr = reinterpret_cast<float2 *>(sScr + vw * SU_SCR_BYTES) + w * SU_SCR_STRIDE;
+        // a candidate's symbols from the even lag below it (65 16-byte chunks, every 32-byte sector once), L2 -> shared
+        // memory, all in flight at once; the lane pair shares the work
+        auto gather = [&](const float2 *win, int L) {
+            const float2 *src = win + (L & ~1);
+#pragma unroll
+            for (int i = 0; i < 33; i++) {
+                const int ch = 2 * i + comp;
+                if (ch < 65) cp_async16(scr + 2 * ch, src + 2 * ch);
+            }
+        };
+        auto exact_value = [&](int L) {                             // cnormf of the pair's two sums, qpsk.c:75-80
+            const float part = su_exact_sum(scr + (L & 1), comp);
+            const float sq = __fmul_rn(part, part);
+            return __fadd_rn(sq, __shfl_xor_sync(0x3u << (lane & ~1), sq, 1));
+        };
+        // One round (an L2 round trip + 128 dependent adds) serves 16 candidates.  4 % of noise-only windows have a
+        // second candidate -- every other batch has one -- so second candidates are not verified with their batch but
+        // queued, and a full queue is verified in one round of its own; the window's result is then corrected in place
+        // (only this warp ever touches it).  Third and later candidates (0.1 %) are verified at once.
+        int qn = 0;                                                 // queued second candidates, the same in every lane
+        int2 *queue = sh.defer[vw];
+        auto flush = [&]() {
+            su_flush_queue(queue, qn, scr, symbols, symbol_stride, max_index, max_value, lane);
+            qn = 0;
+        };
         for (long n = vw; n < my_batches; n += SU_SLOTS) {
             const long b = blockIdx.x + n * gridDim.x;
             const int slot = (int) (n % SU_LISTS);
@@ -543,9 +604,6 @@ search_umma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride,
             }
             const bool direct = exists && nc >= 1 && nc <= SM_MAX_CAND;
             const float2 *W = symbols + (b * SU_WIN + (exists ? w : 0)) * symbol_stride;
-            // largest exact value, smallest lag among equals == the reference's strict '>' scanning the lags upwards
-            float ev = -1.0f;
-            int ei = 1 << 20;
             auto kth = [&](int k) {                                     // the k-th candidate of this lane's window, in lag order
                 int q = 0, p = k;
 #pragma unroll
@@ -556,48 +614,41 @@ search_umma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride,
                     }
                 return (int) sh.cand[slot][q][w][p];
             };
-            // a candidate's symbols from the even lag below it (65 16-byte chunks, every 32-byte sector once), L2 ->
-            // shared memory, all in flight at once; the lane pair shares the work
-            auto gather = [&](float2 *row, int L) {
-                const float2 *src = W + (L & ~1);
-#pragma unroll
-                for (int i = 0; i < 33; i++) {
-                    const int ch = 2 * i + comp;
-                    if (ch < 65) cp_async16(row + 2 * ch, src + 2 * ch);
-                }
-            };
-            auto take = [&](const float2 *row, int L) {                 // both lanes of the pair end with the same (ev, ei)
-                const float part = su_exact_sum(row + (L & 1), comp);
-                const float sq = __fmul_rn(part, part);
-                const float v = __fadd_rn(sq, __shfl_xor_sync(0x3u << (lane & ~1), sq, 1));       // cnormf, qpsk.c:75-80
-                if (v > ev || (v == ev && L < ei)) {
-                    ev = v;
-                    ei = L;
-                }
-            };
-            // one round per candidate rank (4 % of noise-only windows have a second candidate)
-            int rounds = direct ? nc : 0;
+            // largest exact value, smallest lag among equals == the reference's strict '>' scanning the lags upwards
+            float ev = -1.0f;
+            int ei = 1 << 20;
+            // rounds for candidate ranks 0, 2, 3, ... (rank 1 goes to the queue)
+            int rounds = direct ? (nc >= 3 ? nc : 1) : 0;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, off));
 #pragma unroll 1
             for (int k = 0; k < rounds; k++) {
+                if (k == 1) continue;
                 const bool have = direct && k < nc;
                 const int L = have ? kth(k) : 0;
                 {
                     SU_T0
-                    if (have) gather(scr, L);
+                    if (have) gather(W, L);
                     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
                     __syncwarp();
                     SU_T1(w1)
                 }
                 {
                     SU_T0
-                    if (have) take(scr, L);
+                    if (have) {
+                        const float v = exact_value(L);
+                        if (v > ev || (v == ev && L < ei)) {
+                            ev = v;
+                            ei = L;
+                        }
+                    }
                     __syncwarp();
                     SU_T1(w2)
                 }
                 w3 += 1;
             }
+            const bool second = direct && nc >= 2;
+            const int L1 = second ? kth(1) : 0;
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh.cand_empty[slot]);           // the lists have been read: the slot is free
             if (!(ev > 0.0f)) ei = 0, ev = fmaxf(ev, 0.0f);
@@ -618,7 +669,15 @@ search_umma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride,
                 max_index[b * SU_WIN + w] = ei;
                 max_value[b * SU_WIN + w] = ev;
             }
+            // queue the second candidates (after the window's result is stored: the queue's round corrects it)
+            const unsigned m2 = __ballot_sync(0xffffffffu, second && comp == 0);
+            const int add = __popc(m2);
+            if (qn + add > SU_WIN) flush();
+            if (second && comp == 0) queue[qn + __popc(m2 & ((1u << lane) - 1u))] = make_int2((int) (b * SU_WIN + w), L1);
+            qn += add;
+            __syncwarp();
         }
+        if (qn > 0) flush();
     }
 
 #ifdef SU_PROFILE
