@@ -18,7 +18,8 @@
 //             candidate's sum is then evaluated EXACTLY -- the reference's 128 sequential adds per
 //             component, one lane per (candidate, component) -- and the reference's argmax rule (strict
 //             '>', first maximum wins, initial maximum 0.0f) is applied to the exact values.  More than
-//             MAX_CAND candidates (silence, degenerate inputs) fall back to the full exact search.
+//             MAX_CAND candidates (silence, degenerate inputs) or none at all (NaN / Inf samples) fall back
+//             to the full exact search.
 //
 // The result is therefore bit-identical to sc_search.cuh by construction; the tensor cores only decide
 // WHICH of the exact sums are worth evaluating.
@@ -287,10 +288,12 @@ __device__ __forceinline__ void search_mma_pair(const SearchMmaB &sb, SearchMmaD
         best_val[ww] = __shfl_sync(0xffffffffu, ev, 16 * ww);
         best_idx[ww] = __shfl_sync(0xffffffffu, ei, 16 * ww);
     }
-    // ---- fallback: too many candidates (silence, ties over many lags): the full exact search
+    // ---- fallback: too many candidates (silence, ties over many lags) or none (a NaN or Inf sample poisons the whole
+    // proposal, 0 x NaN, while the reference only loses the lags that contain it): the full exact search
 #pragma unroll 1
     for (int ww = 0; ww < 2; ww++) {
-        if (sd.n_cand[ww] > SM_MAX_CAND) search_warp_unpadded(sd.de[ww][0], sd.de[ww][1], lane, best_idx[ww], best_val[ww]);
+        if (sd.n_cand[ww] > SM_MAX_CAND || sd.n_cand[ww] == 0)
+            search_warp_unpadded(sd.de[ww][0], sd.de[ww][1], lane, best_idx[ww], best_val[ww]);
     }
 }
 

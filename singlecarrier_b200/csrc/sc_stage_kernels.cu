@@ -345,7 +345,7 @@ search_fft_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride, 
         int bi;
         float bv;
         search_verify16(sm.de[0], sm.de[1], sm.cand, sm.n_cand, lane, bi, bv);
-        if (sm.n_cand > SM_MAX_CAND) search_warp_unpadded(sm.de[0], sm.de[1], lane, bi, bv);
+        if (sm.n_cand > SM_MAX_CAND || sm.n_cand == 0) search_warp_unpadded(sm.de[0], sm.de[1], lane, bi, bv);   // 0: NaN / Inf samples
         if (lane == 0) {
             max_index[s] = bi;
             max_value[s] = bv;

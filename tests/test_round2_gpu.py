@@ -245,7 +245,7 @@ def test_tensor_core_proposed_search_equals_direct_search(sc, oracle):
     window layout allows it, mma.sync otherwise; both also by name) against the all-exact kernel, bit for
     bit, on 200k windows built to stress the candidate logic: noise only, planted preambles at every lag, several
     equal maxima (ties), silence, one non-zero symbol, tiny and huge amplitudes, a window repeated with a one-ulp
-    change, and odd window counts / strides."""
+    change, NaN / Inf samples, and odd window counts / strides."""
     import torch
     pv = np.frombuffer((C.c_int8 * 128).in_dll(oracle.lib, "sco_preamblevalues"), np.int8).astype(np.float32)
     rng = np.random.default_rng(42)
@@ -268,6 +268,10 @@ def test_tensor_core_proposed_search_equals_direct_search(sc, oracle):
         sym[k + 250:k + 350] *= np.float32(3e4)                 # int16-scale and beyond
         sym[k + 350:k + 400] = sym[k + 400:k + 450]             # near duplicates ...
         sym[k + 350:k + 400, 77] = np.nextafter(sym[k + 400:k + 450, 77].real, np.float32(9)) + 1j * sym[k + 400:k + 450, 77].imag
+        sym[k + 450, 50] = np.nan                               # a NaN poisons the tensor-core proposal of its whole window
+        sym[k + 451, 200] = np.inf + 0j                         # (0 x NaN): those windows must come out of the exact fallback
+        sym[k + 452] = np.nan
+        sym[k + 453, 255 % stride] = np.nan                     # symbol 255 is read (when it exists) but never used
         d = torch.from_numpy(sym.view(np.float32)).cuda()
         out = {}
         names = ["sc_preamble_search_batch_dev", "sc_preamble_search_fft_batch_dev", "sc_preamble_search_direct_batch_dev",
