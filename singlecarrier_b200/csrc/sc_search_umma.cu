@@ -83,6 +83,7 @@ struct SuShared {
     unsigned long long d_empty[2];                   // epilogue -> MMA warp      (1)
     unsigned long long cand_full[SU_LISTS];          // epilogue -> verify        (1)
     unsigned long long cand_empty[SU_LISTS];         // verify -> epilogue        (1)
+    unsigned long long gathered[SU_SLOTS];           // TMA -> verify warp: the candidates' symbols have landed (1 + bytes)
     uint32_t tmem_base;
     uint32_t warp_max[2][SU_EPI_WARPS][SU_WIN];      // per epilogue set
     float part_abs[4][SU_STG_WARPS][SU_WIN];         // sum(|d| + |e|) per staging warp and window, slot n % 4
@@ -347,6 +348,7 @@ search_umma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride,
             mbar_init(&sh.cand_full[i], 1);
             mbar_init(&sh.cand_empty[i], 1);
         }
+        for (int i = 0; i < SU_SLOTS; i++) mbar_init(&sh.gathered[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -586,6 +588,7 @@ search_umma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride,
         // queued, and a full queue is verified in one round of its own; the window's result is then corrected in place
         // (only this warp ever touches it).  Third and later candidates (0.1 %) are verified at once.
         int qn = 0;                                                 // queued second candidates, the same in every lane
+        uint32_t gphase = 0;                                        // parity of the next gather's mbarrier phase
         int2 *queue = sh.defer[vw];
         auto flush = [&]() {
             su_flush_queue(queue, qn, scr, symbols, symbol_stride, max_index, max_value, lane);
@@ -627,10 +630,15 @@ search_umma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride,
                 const bool have = direct && k < nc;
                 const int L = have ? kth(k) : 0;
                 {
+                    // the candidates' symbols from the even lag below each (130 symbols = 1,040 bytes, 16-byte aligned):
+                    // one TMA bulk copy per candidate, L2 -> shared memory
                     SU_T0
-                    if (have) gather(W, L);
-                    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+                    const unsigned hm = __ballot_sync(0xffffffffu, have && comp == 0);
+                    if (lane == 0) mbar_expect_tx(&sh.gathered[vw], (uint32_t) __popc(hm) * (uint32_t) (SU_SCR_STRIDE * 8));
                     __syncwarp();
+                    if (have && comp == 0) tma_bulk_g2s(scr, W + (L & ~1), SU_SCR_STRIDE * 8, &sh.gathered[vw]);
+                    mbar_wait(&sh.gathered[vw], gphase);
+                    gphase ^= 1u;
                     SU_T1(w1)
                 }
                 {
