@@ -19,7 +19,8 @@
 //                       D[128 x 64] fp32 in tensor memory; tcgen05.commit signals an mbarrier;
 //       2 x 4 epilogue  thread = lag: tcgen05.ld of its 64 accumulators, |re|^2 + |im|^2 for the 16 windows, redux.sync
 //         warps         maxima, the bound's threshold, candidate lists by ballot;
-//       3 verify warps  lane = (window, component): the candidate's 128 symbols L2 -> shared memory by cp.async, the
+//       3 verify warps  lane = (window, component): the candidate's 130 symbols L2 -> shared memory by one TMA bulk
+//                       copy each (33 cp.async per lane cost the warp 13 % of the kernel's time), the
 //                       reference's 128 sequential adds, the reference's argmax rule; second candidates are queued
 //                       and verified 16 at a time; the rare fallbacks (no or too many candidates) run the full
 //                       exact search;
@@ -28,8 +29,8 @@
 //     A from shared memory through a descriptor -- slice s of the Toeplitz matrix is a 368 x 16 master read from row
 //     240 - 16 s on, so 11.5 KB served all 16 slices -- correct, but slower.)
 //
-// Measured (tools/umma_bench.py, 2^20 windows): 0.59 ms with a preamble in every window, 0.64 ms on noise-only windows
-// (4 % of which have a second candidate) -- 56 % / 52 % of the measured HBM peak, against 0.99 ms for the mma.sync
+// Measured (tools/umma_bench.py, 2^20 windows): 0.51 ms with a preamble in every window, 0.56 ms on noise-only windows
+// (4 % of which have a second candidate) -- 65 % / 60 % of the measured HBM peak, against 0.99 ms for the mma.sync
 // kernel (shared-memory pipe at 85 %) and 1.45 ms for the all-exact one.  What bounds it now is spread over the roles
 // (make SU_DEFS=-DSU_PROFILE + tools/umma_prof.py shows where each waits): every role is one warp per scheduler
 // running dependent code.
@@ -200,11 +201,11 @@ __device__ __forceinline__ float su_exact_sum(const float2 *__restrict__ X, int 
 #pragma unroll
             for (int i = 0; i < 16; i++) nxt[i] = X[blk + 16 + i];
         }
+        float x[16];                                                // d or e of the block first: the chain below is adds only
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const float x = __fadd_rn(cur[i].x, __uint_as_float(__float_as_uint(cur[i].y) ^ flip));
-            a = pre_neg(blk + i) ? __fsub_rn(a, x) : __fadd_rn(a, x);
-        }
+        for (int i = 0; i < 16; i++) x[i] = __fadd_rn(cur[i].x, __uint_as_float(__float_as_uint(cur[i].y) ^ flip));
+#pragma unroll
+        for (int i = 0; i < 16; i++) a = pre_neg(blk + i) ? __fsub_rn(a, x[i]) : __fadd_rn(a, x[i]);
 #pragma unroll
         for (int i = 0; i < 16; i++) cur[i] = nxt[i];
     }
