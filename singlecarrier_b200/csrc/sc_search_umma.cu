@@ -599,6 +599,9 @@ search_umma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride,
             const long b = blockIdx.x + n * gridDim.x;
             const int slot = (int) (n % SU_LISTS);
             { SU_T0 mbar_wait(&sh.cand_full[slot], (uint32_t) (n / SU_LISTS) & 1u); SU_T1(w0) }
+#ifdef SU_PROFILE
+            const long long tv0 = clock64();
+#endif
             const bool exists = b * SU_WIN + w < n_streams;
             int cnt[SU_EPI_WARPS], nc = 0;
 #pragma unroll
@@ -625,6 +628,9 @@ search_umma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride,
             int rounds = direct ? (nc >= 3 ? nc : 1) : 0;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, off));
+#ifdef SU_PROFILE
+            w3 += clock64() - tv0;
+#endif
 #pragma unroll 1
             for (int k = 0; k < rounds; k++) {
                 if (k == 1) continue;
@@ -654,8 +660,10 @@ search_umma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride,
                     __syncwarp();
                     SU_T1(w2)
                 }
-                w3 += 1;
             }
+#ifdef SU_PROFILE
+            const long long tv1 = clock64();
+#endif
             const bool second = direct && nc >= 2;
             const int L1 = second ? kth(1) : 0;
             __syncwarp();
@@ -685,6 +693,9 @@ search_umma_batch_kernel(const float2 *__restrict__ symbols, long symbol_stride,
             if (second && comp == 0) queue[qn + __popc(m2 & ((1u << lane) - 1u))] = make_int2((int) (b * SU_WIN + w), L1);
             qn += add;
             __syncwarp();
+#ifdef SU_PROFILE
+            w4 += clock64() - tv1;
+#endif
         }
         if (qn > 0) flush();
     }
