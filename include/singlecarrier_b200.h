@@ -102,6 +102,7 @@ uint64_t sc_launch_count(void);
 #define SC_OPT_FE_SEARCH     4
 #define SC_FE_SEARCH_DIRECT  0   /* all 128 lags with the exact sequential sums                                   */
 #define SC_FE_SEARCH_MMA     1   /* proposed on the tensor cores, the candidates verified with the exact sums      */
+#define SC_FE_SEARCH_TCGEN05 2   /* the same with tcgen05.mma / tensor memory, 8 stream-frames per CTA             */
 /* SC_OPT_TRACKER: which kernel runs the per-stream equalizer loop.  Identical results either way: the lane-
  * cooperative kernel executes the same operations in the same order, 16 lanes per stream, and is what makes a
  * bank too small to fill the GPU with one thread per stream 3x faster per call. */

@@ -55,6 +55,15 @@ cudaError_t launch_search_mma_batch(long n_streams, const float2 *symbols, long 
 void search_fft_make_table(float *table /* [8][32][2] */);
 cudaError_t launch_search_fft_batch(long n_streams, const float2 *symbols, long symbol_stride, const float2 *tw,
                                     const void *ptab, int *max_index, float *max_value, cudaStream_t st);
+// sc_frontend_umma.cu: the fused front-end with the search proposed on tcgen05 (SC_FE_SEARCH_TCGEN05); non-overlapped
+// chains and 4-byte aligned frames only (frontend_umma_eligible), bit-identical to launch_frontend
+constexpr int SU_A_ROWS = 368;                       // master rows r = -240 .. 127 of M[r][k] = pre[k - r]
+constexpr int SU_A_WORDS4 = 2 * ((SU_A_ROWS + 7) / 8) * 128 / 16;   // 16-byte words of the master (11,776 bytes)
+void search_umma_make_master(uint16_t *table /* [SU_A_WORDS4 * 8] */);
+bool frontend_umma_eligible(const int16_t *in, long stream_stride);
+cudaError_t launch_frontend_umma(bool wide, const int16_t *in, long stream_stride, const float2 *mix_table,
+                                 const int *timing_cur, const int *timing_next, float2 *win, int *max_index,
+                                 float *max_value, int n_streams, cudaStream_t st, const void *a_master);
 // sc_search_umma.cu: the same search with the proposer on tcgen05 / tensor memory and TMA bulk loads
 bool search_umma_eligible(const float2 *symbols, long symbol_stride);
 cudaError_t launch_search_umma_batch(long n_streams, const float2 *symbols, long symbol_stride,

@@ -21,7 +21,7 @@ PACKET_SAMPLES = 1880
 OPT_SLAB_PARTS, OPT_PROFILE, OPT_H2D_MODE, OPT_FE_SEARCH, OPT_TRACKER, OPT_OVERLAP = 1, 2, 3, 4, 5, 6
 OVERLAP_AUTO, OVERLAP_OFF, OVERLAP_ON, OVERLAP_MAX = 0, 1, 2, 32768
 TRACKER_AUTO, TRACKER_THREAD, TRACKER_COOP, TRACKER_COOP_MAX = 0, 1, 2, 1024
-FE_SEARCH_DIRECT, FE_SEARCH_MMA = 0, 1
+FE_SEARCH_DIRECT, FE_SEARCH_MMA, FE_SEARCH_TCGEN05 = 0, 1, 2
 H2D_COLUMNS, H2D_ROWS, H2D_FULL, H2D_COLUMNS_3D = 0, 1, 2, 3
 N_COUNTERS, N_BER_COUNTERS = 16, 8
 REFERENCE_GAP = 903         # dead air between packets in the reference's main(), qpsk.c:410-412

@@ -302,12 +302,16 @@ def test_tensor_core_proposed_search_equals_direct_search(sc, oracle):
             assert ai[s] == oi and av[s].view(np.uint32) == np.float32(ov).view(np.uint32), s
 
 
-def test_frontend_tensor_core_search_mode_is_bit_identical(sc, oracle):
-    """SC_OPT_FE_SEARCH = SC_FE_SEARCH_MMA: the fused front-end proposes the preamble search on the tensor cores and
-    verifies the candidates exactly; every field of every call equals the default (all-exact) mode and the oracle,
-    on noisy loop-back streams, silence, dead air with exact zeros (many equal correlations) and an odd bank size."""
+@pytest.mark.parametrize("mode_name", ["FE_SEARCH_MMA", "FE_SEARCH_TCGEN05"])
+def test_frontend_tensor_core_search_mode_is_bit_identical(sc, oracle, mode_name):
+    """SC_OPT_FE_SEARCH = SC_FE_SEARCH_MMA / SC_FE_SEARCH_TCGEN05: the fused front-end proposes the preamble search on
+    the tensor cores (mma.sync per warp pair; tcgen05.mma / tensor memory per 8-warp CTA) and verifies the candidates
+    exactly; every field of every call equals the default (all-exact) mode and the oracle, on noisy loop-back streams,
+    silence, dead air with exact zeros (many equal correlations) and an odd bank size."""
     from helpers import compare_results, oracle_results
-    from singlecarrier_b200.modem import FE_SEARCH_MMA, OPT_FE_SEARCH
+    from singlecarrier_b200 import modem
+    from singlecarrier_b200.modem import OPT_FE_SEARCH
+    mode = getattr(modem, mode_name)
     rng = np.random.default_rng(1234)
     ns, nf = 301, 12
     samples = synth_streams(oracle, rng, ns, nf)
@@ -315,23 +319,23 @@ def test_frontend_tensor_core_search_mode_is_bit_identical(sc, oracle):
     samples[8, 5000:] = 0
     samples[9] = (rng.integers(-3, 4, samples.shape[1])).astype(np.int16)       # near silence (SURVEY pin 7)
     out = {}
-    for mode in (0, FE_SEARCH_MMA):
+    for md in (0, mode):
         bank = sc.ModemBank(ns, debug_eq=True)
-        bank.set_option(OPT_FE_SEARCH, mode)
-        out[mode] = bank.rx_frames_host(samples, nf)
+        bank.set_option(OPT_FE_SEARCH, md)
+        out[md] = bank.rx_frames_host(samples, nf)
         bank.close()
-    assert out[0][0].tobytes() == out[FE_SEARCH_MMA][0].tobytes()
-    assert out[0][1].tobytes() == out[FE_SEARCH_MMA][1].tobytes()
+    assert out[0][0].tobytes() == out[mode][0].tobytes()
+    assert out[0][1].tobytes() == out[mode][1].tobytes()
     # the proposer's table is a process-wide cache: releasing it between two batches of a live handle is harmless
     bank = sc.ModemBank(ns, debug_eq=True)
-    bank.set_option(OPT_FE_SEARCH, FE_SEARCH_MMA)
+    bank.set_option(OPT_FE_SEARCH, mode)
     a = bank.rx_frames_host(np.ascontiguousarray(samples[:, : 6 * 1880]), 6)
     sc._lib.check(sc.lib.sc_release_caches())
     b = bank.rx_frames_host(np.ascontiguousarray(samples[:, 6 * 1880:]), nf - 6)
     bank.close()
     assert np.concatenate([a[0], b[0]], axis=1).tobytes() == out[0][0].tobytes()
     obits, ostats = oracle_results(oracle, samples, nf)
-    assert compare_results(out[FE_SEARCH_MMA][0], out[FE_SEARCH_MMA][1], obits, ostats) == []
+    assert compare_results(out[mode][0], out[mode][1], obits, ostats) == []
 
 
 def test_lane_cooperative_tracker_is_bit_identical(sc, oracle):
