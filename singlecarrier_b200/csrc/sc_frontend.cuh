@@ -63,7 +63,8 @@ __device__ __forceinline__ void fe_load(uint32_t (&raw)[FE_KN], const uint32_t *
     }
 }
 
-template <int K_LO>
+// TAB_SHARED: the phasor table lies in shared memory (frontend_umma_kernel stages the call's table once per CTA)
+template <int K_LO, bool TAB_SHARED = false>
 __device__ __forceinline__ void fe_stage(float2 *__restrict__ buf, const uint32_t (&rawk)[FE_KN],
                                          const float2 *__restrict__ tab, int lane, int off) {
     // off = front - shift - h0 is even (front is chosen per pass to make it so), hence every pair
@@ -81,7 +82,8 @@ __device__ __forceinline__ void fe_stage(float2 *__restrict__ buf, const uint32_
         if (K_LO == FE_KB_LO && k == FE_KB_LO) ok = d >= 0;
         if (K_LO == FE_KB_LO && k == FE_KB_HI) ok = p < FE_NPAIR;
         if (ok) {
-            const float4 ph = __ldg(reinterpret_cast<const float4 *>(tab + 2 * p));
+            const float4 ph = TAB_SHARED ? *reinterpret_cast<const float4 *>(tab + 2 * p)
+                                         : __ldg(reinterpret_cast<const float4 *>(tab + 2 * p));
             const float v0 = (float) (int16_t) (raw[kk] & 0xffffu);
             const float v1 = (float) (int16_t) (raw[kk] >> 16);
             *reinterpret_cast<float4 *>(buf + d) = make_float4(__fmul_rn(ph.x, v0), __fmul_rn(ph.y, v0),     // qpsk.c:141

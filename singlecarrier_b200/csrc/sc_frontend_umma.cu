@@ -61,6 +61,7 @@ constexpr uint32_t FU_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (
 
 struct FuShared {
     unsigned long long a_full;                       // TMA -> issuers: the master has landed (1 + bytes)
+    unsigned long long tab_full;                     // TMA -> FIR warps: the phasor table has landed (1 + bytes)
     unsigned long long w_full;                       // FIR warps -> search warps: the batch's windows are written (16)
     unsigned long long w_empty;                      // search warps -> FIR warps: ... and have been consumed (4)
     unsigned long long mma_done;                     // tcgen05.commit -> search warps
@@ -77,7 +78,10 @@ struct FuShared {
 constexpr int FU_OFF_B = FU_A_BYTES;
 constexpr int FU_OFF_W = FU_OFF_B + FU_B_BYTES;
 constexpr int FU_OFF_MIX = FU_OFF_W + FU_WIN * FU_W_BYTES;
-constexpr int FU_OFF_CTRL = FU_OFF_MIX + FU_WIN * FU_MIX_BYTES;
+constexpr int FU_TAB_BYTES = FRAME * 8;               // the call's phasor table, 15,040 bytes (shared by every stream)
+constexpr int FU_OFF_TAB = FU_OFF_MIX + FU_WIN * FU_MIX_BYTES;
+constexpr int FU_OFF_CTRL = FU_OFF_TAB + FU_TAB_BYTES;
+static_assert(FU_OFF_TAB % 16 == 0 && FU_TAB_BYTES % 16 == 0, "TMA bulk copy of the table");
 static_assert(FU_OFF_B % 128 == 0 && FU_OFF_W % 128 == 0 && FU_OFF_MIX % 16 == 0 && FU_OFF_CTRL % 16 == 0, "alignment");
 constexpr int FU_SMEM = FU_OFF_CTRL + (int) sizeof(FuShared) + 1024;
 static_assert(FU_SMEM <= 227 * 1024, "one CTA per SM");
@@ -110,6 +114,14 @@ __device__ __forceinline__ void srch_bar() { asm volatile("bar.sync 1, 128;" :::
 #define FU_T(acc)
 #endif
 
+// a global load that stays where it is written (the compiler otherwise sinks the rx_timing loads, which are issued a
+// frame ahead on purpose, down to their use)
+__device__ __forceinline__ int ld_pinned(const int *p) {
+    int v;
+    asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 template <bool WIDE>
 __global__ void __launch_bounds__(FU_THREADS, 1)
 frontend_umma_kernel(const int16_t *__restrict__ in, long stream_stride, const float2 *__restrict__ mix_table,
@@ -131,6 +143,7 @@ frontend_umma_kernel(const int16_t *__restrict__ in, long stream_stride, const f
     // ---- set-up: barriers, tensor memory, the master of the A operand (TMA, lands during the first FIR)
     if (tid == 0) {
         mbar_init(&sh.a_full, 1);
+        mbar_init(&sh.tab_full, 1);
         mbar_init(&sh.w_full, FU_WIN);
         mbar_init(&sh.w_empty, FU_SRCH_WARPS);
         mbar_init(&sh.mma_done, 1);
@@ -148,6 +161,8 @@ frontend_umma_kernel(const int16_t *__restrict__ in, long stream_stride, const f
     if (tid == 0) {
         mbar_expect_tx(&sh.a_full, (uint32_t) FU_A_BYTES);
         tma_bulk_g2s(sA, a_master, (uint32_t) FU_A_BYTES, &sh.a_full);
+        mbar_expect_tx(&sh.tab_full, (uint32_t) FU_TAB_BYTES);
+        tma_bulk_g2s(fu_smem + FU_OFF_TAB, mix_table, (uint32_t) FU_TAB_BYTES, &sh.tab_full);
     }
     const uint32_t tmem = sh.tmem_base;
 #ifdef FU_PROFILE
@@ -164,7 +179,8 @@ frontend_umma_kernel(const int16_t *__restrict__ in, long stream_stride, const f
         // previous frame's second FIR pass.
         auto stream_of = [&](long n) { return (blockIdx.x + n * gridDim.x) * FU_WIN + warp; };
         int shift = 0, base2 = 0;
-        const float2 *tab = mix_table;
+        const float2 *const tab_s = reinterpret_cast<const float2 *>(fu_smem + FU_OFF_TAB);
+        const float2 *tab = tab_s;
         const uint32_t *fp = nullptr;
         uint32_t raw[FE_KN];
 #pragma unroll
@@ -174,25 +190,26 @@ frontend_umma_kernel(const int16_t *__restrict__ in, long stream_stride, const f
             base2 = base & ~1;
             shift = base - base2;
             fp = reinterpret_cast<const uint32_t *>(in + sx * stream_stride + base2);
-            tab = mix_table + base2;
+            tab = tab_s + base2;
         };
         long s = stream_of(0);
         bool active = my_batches > 0 && s < n_streams;
         if (active) {
-            setup(s, timing_cur[s]);
+            setup(s, ld_pinned(timing_cur + s));
             fe_load<FE_KA_LO>(raw, fp, lane, base2);
         }
         long s_nx = stream_of(1);
         bool act_nx = my_batches > 1 && s_nx < n_streams;
-        int T_nx = act_nx ? timing_cur[s_nx] : 0;
+        int T_nx = act_nx ? ld_pinned(timing_cur + s_nx) : 0;
+        mbar_wait(&sh.tab_full, 0u);
 #pragma unroll 1
         for (long n = 0; n < my_batches; n++) {
-            const int t2 = active ? timing_next[s] : 0;
+            const int t2 = active ? ld_pinned(timing_next + s) : 0;
             u64 accA[FE_R], accB[FE_R];
             {   // pass A: outputs 0..144
                 const int front = FE_FRONT + (shift & 1);
                 if (active) {
-                    fe_stage<FE_KA_LO>(mix, raw, tab, lane, front - shift);
+                    fe_stage<FE_KA_LO, true>(mix, raw, tab, lane, front - shift);
                     fe_load<FE_KB_LO>(raw, fp, lane, base2);
                 }
                 __syncwarp();
@@ -204,7 +221,7 @@ frontend_umma_kernel(const int16_t *__restrict__ in, long stream_stride, const f
             {   // pass B: outputs 145..289
                 constexpr int h0 = CYC * FE_PASS_OUT;
                 const int front = FE_FRONT + ((shift + h0) & 1);
-                if (active) fe_stage<FE_KB_LO>(mix, raw, tab, lane, front - shift - h0);
+                if (active) fe_stage<FE_KB_LO, true>(mix, raw, tab, lane, front - shift - h0);
                 const bool active_cur = active;
                 s = s_nx;
                 active = act_nx;
@@ -214,7 +231,7 @@ frontend_umma_kernel(const int16_t *__restrict__ in, long stream_stride, const f
                 }
                 s_nx = stream_of(n + 2);
                 act_nx = n + 2 < my_batches && s_nx < n_streams;
-                T_nx = act_nx ? timing_cur[s_nx] : 0;
+                T_nx = act_nx ? ld_pinned(timing_cur + s_nx) : 0;
                 __syncwarp();
 #pragma unroll
                 for (int r = 0; r < FE_R; r++) accB[r] = 0ull;
