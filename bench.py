@@ -355,6 +355,21 @@ def main():
     bank.reset()
     bank.rx_frames_dev(d_in, n_frames, d_res, stream=stream_handle)
     prof = bank.profile_read()
+    # the same pass with the front-end's search proposed on tcgen05 (SC_FE_SEARCH_TCGEN05, opt-in; sc_frontend_umma.cu):
+    # per-launch time of that kernel, and that every result byte is the same
+    from singlecarrier_b200.modem import FE_SEARCH_DIRECT, FE_SEARCH_TCGEN05, OPT_FE_SEARCH
+    res_default = d_res.clone()
+    bank.set_option(OPT_FE_SEARCH, FE_SEARCH_TCGEN05)
+    bank.reset()
+    bank.rx_frames_dev(d_in, min(n_frames, 3), d_res, stream=stream_handle)    # one-time set-up (attributes, the master table)
+    bank.profile_read()
+    bank.reset()
+    bank.rx_frames_dev(d_in, n_frames, d_res, stream=stream_handle)
+    prof_tc = bank.profile_read()
+    fe_tc_ms = prof_tc["frontend_ms"] / max(prof_tc["frontend_launches"], 1)
+    fe_tc_same = bool(torch.equal(res_default, d_res))
+    del res_default
+    bank.set_option(OPT_FE_SEARCH, FE_SEARCH_DIRECT)
     bank.set_option(OPT_PROFILE, 0)
     bank.set_option(OPT_SLAB_PARTS, args.slab_parts)
     fe_ms = prof["frontend_ms"] / max(prof["frontend_launches"], 1)
@@ -383,6 +398,10 @@ def main():
                           "same input right after the timed steps (the timed steps run two slabs on two streams, whose "
                           "launches overlap and cannot be timed individually)")
     roofline["other_kernel"] = other
+    roofline["frontend_tcgen05"] = {
+        "kernel": "frontend_umma_kernel", "ms_per_launch": fe_tc_ms, "identical_results": fe_tc_same,
+        "note": "opt-in mode SC_OPT_FE_SEARCH = SC_FE_SEARCH_TCGEN05 (persistent, 16 FIR warps + 4 search warps per SM, "
+                "proposer on tcgen05.mma, exact verification); not used by the timed steps"}
     chain_gbs = streams * n_frames * CHAIN_BYTES * args.steps / (ms_total * 1e-3) / 1e9
     roofline["chain"] = {"bytes_per_symbol": CHAIN_BYTES / SYM_PER_FRAME, "achieved_gbs": chain_gbs,
                          "frac_of_hbm": chain_gbs / hbm_peak,

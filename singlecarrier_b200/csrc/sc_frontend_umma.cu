@@ -277,7 +277,7 @@ frontend_umma_kernel(const int16_t *__restrict__ in, long stream_stride, const f
         for (long n = 0; n < my_batches; n++) {
             const long s0 = (blockIdx.x + n * gridDim.x) * FU_WIN;
             const uint32_t ph = (uint32_t) n & 1u;
-            mbar_wait(&sh.w_full, ph);
+            mbar_wait_relaxed(&sh.w_full, ph);          // ~20 % of a search warp's time: no hurry, the FIR warps are the pace
             FU_T(p0)
             // ---- B operand: thread t stages the 8-symbol chunks (t >> 4) + 8 i, i < 4, of window t & 15
 #pragma unroll 1
@@ -534,23 +534,9 @@ cudaError_t launch_frontend_umma(bool wide, const int16_t *in, long stream_strid
         int nb = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, frontend_umma_kernel<false>, FU_THREADS, FU_SMEM);
         if (e != cudaSuccess) return e;
-        if (getenv("SC_FE_UMMA_DEBUG")) {
+        if (nb < 1) return cudaErrorLaunchOutOfResources;
+        if (getenv("SC_FE_UMMA_DEBUG"))
             fprintf(stderr, "frontend_umma_kernel: %d CTAs per SM, %d bytes of shared memory each\n", nb, FU_SMEM);
-            cudaFuncAttributes fa;
-            cudaFuncGetAttributes(&fa, frontend_umma_kernel<false>);
-            cudaDeviceProp pr;
-            cudaGetDeviceProperties(&pr, dev);
-            fprintf(stderr, "  regs %d static smem %zu maxdyn %d carveout %d local %zu | SM: smem %zu regs %d reserved %zu optin %zu\n",
-                    fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.preferredShmemCarveout, fa.localSizeBytes,
-                    pr.sharedMemPerMultiprocessor, pr.regsPerMultiprocessor, pr.reservedSharedMemPerBlock, pr.sharedMemPerBlockOptin);
-            for (int sm = 60000; sm <= 116000; sm += 8000) {
-                int nb2 = 0;
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, frontend_umma_kernel<false>, FU_THREADS, sm);
-                int nb3 = 0;
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb3, frontend_umma_kernel<false>, 256, sm);
-                fprintf(stderr, "  dyn smem %d: %d CTAs of 384 threads, %d of 256\n", sm, nb2, nb3);
-            }
-        }
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
         if (dev < 64) {

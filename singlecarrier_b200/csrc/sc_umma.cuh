@@ -38,6 +38,23 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
     }
 }
 
+// the same for a role with slack: backs off between polls so that the spin does not take issue slots from busy warps
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned long long *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0;; spin++) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        __nanosleep(100);
+        if (spin > (1u << 22)) asm volatile("trap;");
+    }
+}
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))

@@ -97,3 +97,28 @@ def test_tcgen05_search_kernel_uses_the_blackwell_units():
     assert flush and sum("LDGSTS" in i for i in funcs[flush[0]]) >= 33
     assert not [i for i in ins if "FFMA" in i or "HMMA.16816" in i]
     assert sum(bool(re.match(r"(@!?P\d+\s+)?FADD\b", i)) for i in ins) >= 256
+
+
+def test_fused_tcgen05_frontend_uses_the_blackwell_units_and_no_contraction():
+    """frontend_umma_kernel (sc_frontend_umma.cu, SC_FE_SEARCH_TCGEN05): the FIR is the front-end's (packed multiplies
+    with a zero addend, separate packed adds -- nothing contracted); the proposer is tcgen05.mma with both operands
+    through shared-memory descriptors and D in tensor memory (UTCHMMA, LDTM, the allocator's UTCATOMSWS), completion by
+    tcgen05.commit (UTCBAR); the Toeplitz master and the call's phasor table arrive by TMA bulk copies (UBLKCP); the
+    verifier's sums are plain adds."""
+    funcs = sass()
+    names = [n for n in funcs if "frontend_umma_kernel" in n]
+    assert len(names) == 2, names                               # narrow / wide tap table
+    for n in names:
+        ins = funcs[n]
+        for mnem, least in (("UTCHMMA", 1), ("LDTM", 4), ("UTCBAR", 1), ("UBLKCP", 2), ("UTCATOMSWS", 2), ("SYNCS", 6),
+                            ("REDUX", 16)):
+            assert sum(mnem in i for i in ins) >= least, (n, mnem, sum(mnem in i for i in ins))
+        packed = [i for i in ins if "FFMA2" in i]
+        assert len(packed) >= 400, n
+        for i in packed:
+            assert i.rstrip(" ;").endswith(("RZ", "RZ.F32")), (n, i)
+        assert sum("FADD2" in i for i in ins) >= len(packed)
+        # the only scalar multiply-adds allowed are those of the bound's sqrt / none at all (sqrt.approx is a MUFU)
+        assert not [i for i in ins if re.match(r"(@!?P\d+\s+)?FFMA\b", i)], n
+        assert not [i for i in ins if "HMMA.16816" in i], n
+        assert sum(bool(re.match(r"(@!?P\d+\s+)?FADD\b", i)) for i in ins) >= 256
