@@ -8,29 +8,34 @@
 // cores, a rigorous bound, the few lags that can still be the maximum evaluated with the reference's exact 128-term
 // sequential sums -- so max_index / max_value are bit-identical to the all-exact search.
 //
-// Two persistent CTAs per SM, 12 warps each, working on batches of 8 stream-frames:
+// One persistent CTA per SM (a kernel that allocates tensor memory is given one CTA per SM whatever it needs: measured,
+// profiles/r02_fe_tcgen05.md), 20 warps, working on batches of 16 stream-frames:
 //
-//   * warps 0..7 (FIR): one stream-frame each per batch -- global loads, mixing, the two FIR passes in the warp's own
-//     sample buffer, then W[290] into the batch's window buffer and sum(|d| + |e|) for the bound.  They never wait for
-//     the search: the only hand-overs are two mbarriers (windows full / windows free again);
-//   * warps 8..11 (search), one batch behind the FIR warps:
-//       - the 8 windows' d = s.r - s.i, e = s.i + s.r split into two bf16 pieces each and written as ONE B operand,
-//         N = 32 columns (piece p of window w = column 8 p + w) x K = 256 symbols, K-major no-swizzle core matrices; a
-//         quarter-warp handles one 8-symbol chunk of all 8 windows, so its 128-bit loads and stores are conflict-free
+//   * warps 0..15 (FIR): one stream-frame each per batch -- global loads, mixing, the two FIR passes in the warp's own
+//     sample buffer, then W[290] into the batch's window buffer and sum(|d| + |e|) for the bound.  With four warps per
+//     scheduler nothing hides a warp's own latencies, so rx_timing is fetched two batches ahead, pass A's samples
+//     during the previous frame's second FIR pass, and the call's phasor table (15 KB, the same for every stream) lies
+//     in shared memory (one TMA bulk copy per CTA).  The only hand-overs to the search warps are two mbarriers
+//     (windows full / windows free again);
+//   * warps 16..19 (search), one batch behind the FIR warps:
+//       - the 16 windows' d = s.r - s.i, e = s.i + s.r split into two bf16 pieces each and written as ONE B operand,
+//         N = 64 columns (piece p of window w = column 16 p + w) x K = 256 symbols, K-major no-swizzle core matrices; a
+//         quarter-warp handles one 8-symbol chunk of 8 windows, so its 128-bit loads and stores are conflict-free
 //         (the windows lie 16 bytes (mod 128) apart);
 //       - the A operand is the 11.5 KB Toeplitz master (K-step s of P is the master read from row 240 - 16 s on:
 //         another start address in the shared-memory descriptor), brought in once per CTA by a TMA bulk copy;
-//       - two threads issue 8 tcgen05.mma each (M = 128 lags, N = 32, K = 16), the two K halves accumulating in two
-//         32-column accumulators in tensor memory; tcgen05.commit on an mbarrier;
-//       - epilogue, thread = lag (warp % 4 = tensor-memory lane quarter): tcgen05.ld, |re|^2 + |im|^2 for the 8
+//       - one thread issues 16 tcgen05.mma (M = 128 lags, N = 64, K = 16), D fp32 in tensor memory; tcgen05.commit
+//         on an mbarrier;
+//       - epilogue, thread = lag (warp % 4 = tensor-memory lane quarter): tcgen05.ld, |re|^2 + |im|^2 for the 16
 //         windows, redux.sync maxima, the bound's threshold, candidate lists by ballot;
-//       - ONE warp verifies all 8 windows at once (lane = rank x window x component): 128 shared-memory loads per
-//         batch instead of 135 per window;
-//       - the windows are handed to the tracker in 64-byte segments (8 adjacent streams per row).
+//       - verification, lane = (window, component): search warp q takes the candidates of rank q, q + 4, ... of every
+//         window (128 shared-memory loads per round for 16 windows, against 135 per window in the all-exact search);
+//       - the windows are handed to the tracker in 128-byte segments (16 adjacent streams per row).
 //
-// So the FP32 pipe sees the FIR's 16 warps without interruption, and the search costs the SM ~350 issue slots per
-// stream-frame instead of ~1,300.  (First form, 62d71ad: one role per CTA, 8 warps doing everything in turn -- the
-// serial tail of MMA, epilogue, verification and window write left the FP32 pipe idle: 0.530 ms against 0.478 ms.)
+// Measured (profiles/r02_fe_tcgen05.md): 0.469 ms per 131,072 stream-frames against 0.478 ms for frontend_kernel, with
+// a third fewer instructions (270 M against 407 M); the search is off the FP32 and LSU pipes, what remains is the FIR
+// with 16 warps per SM (6.7 KB of private buffer each limits their number).  Earlier forms: one role per CTA
+// (62d71ad, 0.530 ms), 8 + 4 warps (0.537), before the latency fixes (0.526 / 0.502).
 #include "sc_common.cuh"
 #include "sc_tables.cuh"
 #include "sc_frontend.cuh"
