@@ -25,3 +25,6 @@ python bench.py --no-e2e --no-cpu 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']; o=r['other_kernel']
 print('value %.0f Msym/s  ms/step %.2f | %s %.3f | %s %.3f'%(d['value'],d['ms_per_step'],r['kernel'],r['ms_per_launch'],o['kernel'],o['ms_per_launch']))"
+# the opt-in fused tcgen05 front-end: A/B against the default, then one full capture (tools/ncu_extract.py reads it)
+bash tools/fe_umma_ab.sh > gpurun_out/fe_umma_ab_$R.txt 2>&1
+SC_FE_SEARCH=tcgen05 ncu --set full --clock-control none --import-source on -k regex:frontend_umma_kernel -s 10 -c 1 -o gpurun_out/prof_fe_umma_$R $CMD2 > gpurun_out/ncu_fe_umma.log 2>&1
